@@ -1,0 +1,132 @@
+/* reve_cuda.h -- C ABI of libreve_cuda: the B200-native (sm_100a) replacement for what REVE
+ * reaches through `Command::new("realesrgan-ncnn-vulkan")`.
+ *
+ * What it replaces in the reference (ONdraid/reve; paths relative to the reference root):
+ *   - reve-shared/src/lib.rs:129-155  Video::upscale_segment: spawns the upscaler once per
+ *     segment with `-i temp\tmp_frames\{i} -o temp\out_frames\{i} -n realesr-animevideov3-x2
+ *     -s {scale} -f png -v` and returns its stderr.
+ *   - reve-cli/src/main.rs:262-273    the caller blocks on that reader and counts "done" lines.
+ *   - reve-gui/src-tauri/src/commands.rs:52-64  the GUI's spawn of the same binary.
+ * The reference has a process boundary there, not an FFI; this header is the FFI a Rust crate
+ * (`reve-upscale`) binds instead.  Data at the boundary: packed 8-bit RGB,
+ * HWC, row stride in bytes, origin top-left (what ffmpeg's PNG / rgb24 export holds); output is
+ * (W*s) x (H*s) in the same layout.  No alpha, no 16-bit.
+ *
+ * Conventions: every function returns 0 (REVE_OK) or a negative reve_status; the message of the
+ * last failure on a context is available through reve_last_error(ctx) (or reve_last_error(NULL)
+ * for failures of functions that have no context).  No C++ exception crosses this boundary.
+ * There is no CPU fallback: on a machine without an sm_100 device every compute entry point
+ * fails with REVE_E_ARCH / REVE_E_CUDA.
+ *
+ * Threading: a reve_ctx is bound to one device and is NOT thread-safe (Rust: Send, !Sync);
+ * distinct contexts may be driven concurrently from distinct host threads (one per GPU).
+ * A reve_model is immutable after creation and may be shared by any number of contexts.
+ * The library spawns no host threads.
+ */
+#ifndef REVE_CUDA_H
+#define REVE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REVE_VERSION 100 /* 0.1.0 */
+
+typedef enum reve_status {
+    REVE_OK = 0,
+    REVE_E_INVAL = -1, /* bad argument */
+    REVE_E_NOMEM = -2, /* host or device allocation failed */
+    REVE_E_CUDA = -3,  /* CUDA runtime/driver error (incl. no device) */
+    REVE_E_IO = -4,    /* file could not be read / written */
+    REVE_E_MODEL = -5, /* .param/.bin is not a realesr-animevideov3 (SRVGGNetCompact) model */
+    REVE_E_ARCH = -6,  /* device is not compute capability 10.x (sm_100) */
+    REVE_E_BUSY = -7,  /* submit ring full: call reve_wait first */
+    REVE_E_EMPTY = -8  /* reve_wait with nothing in flight */
+} reve_status;
+
+typedef struct reve_model reve_model;
+typedef struct reve_ctx reve_ctx;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int reve_version(void);
+const char* reve_strerror(int status);
+/* Message of the last failure on `ctx` (ctx == NULL: last failure of a context-free call on this
+ * thread).  Never NULL; valid until the next failing call on the same context / thread. */
+const char* reve_last_error(const reve_ctx* ctx);
+/* Number of CUDA devices that can run the kernels (compute capability 10.x). */
+int reve_device_count(int* n);
+
+/* ---- model (replaces `-n realesr-animevideov3-x{s}` + the models\ directory) ---------------- */
+/* Parse an ncnn .param/.bin pair and validate that it is SRVGGNetCompact(3->64, 16 body convs,
+ * 64->3*s*s, PReLU, PixelShuffle(s) + nearest residual).  fp16-tagged and raw fp32 payloads. */
+int reve_model_load_ncnn(const char* param_path, const char* bin_path, reve_model** out);
+/* Seeded He-normal random init of the named architecture (used when the weight files are
+ * absent offline).  Bit-identical to oracle/srvgg.py:make_weights(scale, seed). */
+int reve_model_random(int scale, uint64_t seed, reve_model** out);
+/* Write the model as ncnn .param/.bin (fp16 != 0: tag 0x01306B47 payload). */
+int reve_model_save_ncnn(const reve_model* m, const char* param_path, const char* bin_path, int fp16);
+int reve_model_info(const reve_model* m, int* scale, int* num_feat, int* num_conv);
+void reve_model_free(reve_model* m);
+
+/* ---- context (one per GPU; owns streams, device buffers, tensor maps) ----------------------- */
+/* in_w x in_h: input frame size.  tile: 0 = whole frame, T > 0 = upstream tile size (the spawned
+ * binary uses 200 on any device with > 1.9 GB).  prepad: upstream uses 10.  ring_depth: frames
+ * that may be in flight between reve_submit and reve_wait (1..16). */
+int reve_ctx_create(int device, const reve_model* m, int in_w, int in_h, int tile, int prepad,
+                    int ring_depth, reve_ctx** out);
+void reve_ctx_destroy(reve_ctx* ctx);
+/* Geometry of the context: output frame size and scale. */
+int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale);
+
+/* Pinned host memory for frame buffers (plain malloc'ed buffers work too, but copy slower and
+ * do not overlap). */
+int reve_host_alloc(size_t bytes, void** out);
+void reve_host_free(void* p);
+
+/* Asynchronous frame: H2D copy -> kernels -> D2H copy on the context's streams.  The caller keeps
+ * rgb_in / rgb_out valid until the matching reve_wait.  Strides in bytes (>= 3*w). */
+int reve_submit(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, uint8_t* rgb_out,
+                size_t out_stride, uint64_t tag);
+/* Blocks until the oldest submitted frame is complete (FIFO) and returns its tag. */
+int reve_wait(reve_ctx* ctx, uint64_t* tag);
+/* Blocks until everything submitted on the context has finished. */
+int reve_sync(reve_ctx* ctx);
+
+/* Device-resident variant (kernel-only benchmarks, or callers that already hold frames on the
+ * GPU): d_in = n_frames packed frames (3*in_w*in_h bytes each), d_out likewise at output size.
+ * Enqueued on the context's compute stream; returns without synchronising. */
+int reve_upscale_device(reve_ctx* ctx, const void* d_in, void* d_out, int n_frames);
+/* The context's compute stream (a cudaStream_t), for callers that time with their own events. */
+int reve_ctx_stream(const reve_ctx* ctx, void** stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+typedef struct reve_profile {
+    uint64_t launches_conv0, launches_body, launches_tail; /* kernels launched since reset */
+    double ms_conv0, ms_body, ms_tail; /* summed CUDA-event time; only while profiling is on */
+    uint64_t timed_body;               /* body launches covered by ms_body */
+    uint64_t timed_frames;
+} reve_profile;
+/* on != 0: bracket every kernel launch with CUDA events (slower; for roofline measurements). */
+int reve_ctx_set_profiling(reve_ctx* ctx, int on);
+/* Synchronises the compute stream, then fills *out; reset != 0 clears the counters. */
+int reve_ctx_get_profile(reve_ctx* ctx, reve_profile* out, int reset);
+
+/* Test hook: run the network on one frame and copy out the fp16 NHWC feature canvas after
+ * `layer` convolutions+PReLU (1..17) as float32 [canvas_h][canvas_w][64] into `out`
+ * (cap_floats = capacity).  canvas_w/h may be NULL.  Used by the per-layer parity tests. */
+int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, int layer,
+                        float* out, size_t cap_floats, int* canvas_w, int* canvas_h);
+/* Canvas geometry tables (context-free, host only; test hook): the canvas is the side-by-side
+ * layout of upstream's padded tiles.  For canvas column/row i: the source frame coordinate feeding
+ * it (reflect-101 applied; -1 for a gap) and the output coordinate at input resolution (-1 if
+ * cropped).  Arrays may be NULL; cap = capacity of each non-NULL array in ints. */
+int reve_geometry(int in_w, int in_h, int scale, int tile, int prepad, int* canvas_w, int* canvas_h,
+                  int* src_x, int* out_x, int* src_y, int* out_y, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVE_CUDA_H */

@@ -1,0 +1,11 @@
+"""reve_b200 -- B200-native (sm_100a) implementation of REVE's per-segment upscale step.
+
+The product is ``libreve_cuda.so`` (hand-written CUDA behind the C ABI in ``include/reve_cuda.h``);
+this package is the thin Python host mirror used by the tests and ``bench.py``.  It never falls
+back to a CPU path: if the shared library or an sm_100 device is missing, it raises.
+"""
+from .upscaler import (Model, Upscaler, ReveError, load_library, library_path, geometry,
+                       upscale_segment)
+
+__all__ = ["Model", "Upscaler", "ReveError", "load_library", "library_path", "geometry",
+           "upscale_segment"]

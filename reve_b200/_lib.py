@@ -1,0 +1,64 @@
+"""ctypes binding of include/reve_cuda.h (exactly the symbols the header declares)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libreve_cuda.so")
+
+
+class reve_profile(C.Structure):
+    _fields_ = [("launches_conv0", C.c_uint64), ("launches_body", C.c_uint64),
+                ("launches_tail", C.c_uint64), ("ms_conv0", C.c_double), ("ms_body", C.c_double),
+                ("ms_tail", C.c_double), ("timed_body", C.c_uint64), ("timed_frames", C.c_uint64)]
+
+
+# name -> (restype, argtypes); mirrors include/reve_cuda.h one to one
+SIGNATURES = {
+    "reve_version": (C.c_int, []),
+    "reve_strerror": (C.c_char_p, [C.c_int]),
+    "reve_last_error": (C.c_char_p, [C.c_void_p]),
+    "reve_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "reve_model_load_ncnn": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "reve_model_random": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "reve_model_save_ncnn": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "reve_model_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "reve_model_free": (None, [C.c_void_p]),
+    "reve_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_void_p)]),
+    "reve_ctx_destroy": (None, [C.c_void_p]),
+    "reve_ctx_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
+    "reve_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "reve_host_free": (None, [C.c_void_p]),
+    "reve_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64]),
+    "reve_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "reve_sync": (C.c_int, [C.c_void_p]),
+    "reve_upscale_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "reve_ctx_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "reve_ctx_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "reve_ctx_get_profile": (C.c_int, [C.c_void_p, C.POINTER(reve_profile), C.c_int]),
+    "reve_debug_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "reve_geometry": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 2 + [C.c_void_p] * 4 + [C.c_size_t]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libreve_cuda.so from the package directory.  No fallback: a missing library is an
+    error (build it with ``python -c 'import __graft_entry__ as g; g.build()'`` or
+    ``make -C reve_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build the CUDA extension first "
+                              "(make -C reve_b200/csrc); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,612 @@
+// C ABI of libreve_cuda (include/reve_cuda.h): context, staging ring and the per-frame launch
+// sequence.  This is what stands behind Video::upscale_segment in place of the spawned
+// `realesrgan-ncnn-vulkan` process (reference reve-shared/src/lib.rs:129-155).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/reve_cuda.h"
+#include "geometry.h"
+#include "kernels.h"
+#include "model.h"
+
+using namespace reve;
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Slot {
+    uint8_t* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_done = nullptr;
+    uint64_t tag = 0;
+};
+
+struct ProfEvent {
+    int kind;  // 0 conv0, 1 body, 2 tail, -1 frame start marker
+    cudaEvent_t ev;
+};
+
+}  // namespace
+
+struct reve_ctx {
+    int device = 0;
+    int sm_count = 0;
+    Geometry g;
+    int scale = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    __half* act[2] = {nullptr, nullptr};
+    size_t act_bytes = 0;
+    uint8_t *d_colflag = nullptr, *d_rowflag = nullptr;
+    int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr;
+    void* d_wblob[kNumConv] = {};
+    CUtensorMap map_in[2], map_out[2];
+    Conv0Params c0;
+    ConvParams body[kNumBody];
+    ConvParams tail;
+    int grid = 0;
+    DebugBlock* dbg_host = nullptr;
+    DebugBlock* dbg_dev = nullptr;
+    std::vector<Slot> ring;
+    int head = 0, oldest = 0, inflight = 0;
+    bool profiling = false;
+    std::vector<ProfEvent> prof_events;
+    reve_profile prof = {};
+    mutable std::string err;
+};
+
+namespace {
+
+int set_err(reve_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+std::string cuda_msg(reve_ctx* ctx, const char* what, cudaError_t e) {
+    std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    if (ctx && ctx->dbg_host && ctx->dbg_host->code != 0) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, " [kernel watchdog: wait tag %u timed out in block %u, aux0=%u aux1=%u]",
+                      ctx->dbg_host->code, ctx->dbg_host->block, ctx->dbg_host->aux0, ctx->dbg_host->aux1);
+        m += buf;
+    }
+    return m;
+}
+
+#define CK(ctx, call)                                                         \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return set_err(ctx, REVE_E_CUDA, cuda_msg(ctx, #call, e__)); \
+    } while (0)
+
+int encode_map(reve_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base, int cw, int ch, int box_px) {
+    const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(cw), static_cast<cuuint64_t>(ch)};
+    const cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(cw) * 128};
+    const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_px), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        std::snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        return set_err(ctx, REVE_E_CUDA, buf);
+    }
+    return REVE_OK;
+}
+
+template <typename T>
+int upload(reve_ctx* ctx, T** dptr, const void* src, size_t bytes) {
+    CK(ctx, cudaMalloc(reinterpret_cast<void**>(dptr), bytes));
+    CK(ctx, cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+    return REVE_OK;
+}
+
+void prof_mark(reve_ctx* ctx, int kind) {
+    if (!ctx->profiling) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, ctx->s_comp);
+    ctx->prof_events.push_back({kind, ev});
+}
+
+// Enqueue the 18 launches of one frame on the compute stream.
+int enqueue_frame(reve_ctx* ctx, const uint8_t* d_in, long long in_stride, uint8_t* d_out, long long out_stride,
+                  int stop_after_layers = kNumConv) {
+    prof_mark(ctx, -1);
+    Conv0Params c0 = ctx->c0;
+    c0.src = d_in;
+    c0.src_stride = in_stride;
+    CK(ctx, launch_conv0(ctx->s_comp, c0));
+    ctx->prof.launches_conv0++;
+    prof_mark(ctx, 0);
+    for (int k = 0; k < kNumBody && k + 1 < stop_after_layers; ++k) {
+        CK(ctx, launch_conv_body(ctx->s_comp, ctx->grid, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], ctx->body[k]));
+        ctx->prof.launches_body++;
+        prof_mark(ctx, 1);
+    }
+    if (stop_after_layers >= kNumConv) {
+        ConvParams t = ctx->tail;
+        t.src = d_in;
+        t.src_stride = in_stride;
+        t.dst = d_out;
+        t.dst_stride = out_stride;
+        CK(ctx, launch_conv_tail(ctx->s_comp, ctx->grid, ctx->scale, ctx->map_in[0], t));
+        ctx->prof.launches_tail++;
+        prof_mark(ctx, 2);
+    }
+    return REVE_OK;
+}
+
+int collect_profile(reve_ctx* ctx) {
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    for (size_t i = 1; i < ctx->prof_events.size(); ++i) {
+        const ProfEvent& cur = ctx->prof_events[i];
+        if (cur.kind < 0) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_events[i - 1].ev, cur.ev) != cudaSuccess) continue;
+        if (cur.kind == 0) ctx->prof.ms_conv0 += ms;
+        if (cur.kind == 1) { ctx->prof.ms_body += ms; ctx->prof.timed_body++; }
+        if (cur.kind == 2) { ctx->prof.ms_tail += ms; ctx->prof.timed_frames++; }
+    }
+    for (auto& pe : ctx->prof_events) cudaEventDestroy(pe.ev);
+    ctx->prof_events.clear();
+    return REVE_OK;
+}
+
+void destroy_ctx(reve_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->s_comp) cudaStreamSynchronize(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+    if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+    for (auto& pe : ctx->prof_events) cudaEventDestroy(pe.ev);
+    for (auto& s : ctx->ring) {
+        cudaFree(s.d_in);
+        cudaFree(s.d_out);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    cudaFree(ctx->act[0]);
+    cudaFree(ctx->act[1]);
+    cudaFree(ctx->d_colflag);
+    cudaFree(ctx->d_rowflag);
+    cudaFree(ctx->d_srcx);
+    cudaFree(ctx->d_srcy);
+    cudaFree(ctx->d_outx);
+    cudaFree(ctx->d_outy);
+    for (void* p : ctx->d_wblob) cudaFree(p);
+    if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, int tile, int prepad, int ring_depth) {
+    int ndev = 0;
+    CK(ctx, cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_err(ctx, REVE_E_INVAL, "no such CUDA device");
+    cudaDeviceProp prop;
+    CK(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_err(ctx, REVE_E_ARCH, std::string("device '") + prop.name + "' is not compute capability 10.x (sm_100); there is no fallback path");
+    CK(ctx, cudaSetDevice(device));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->scale = m.scale;
+    std::string gerr;
+    int rc = make_geometry(in_w, in_h, m.scale, tile, prepad, ctx->g, gerr);
+    if (rc != REVE_OK) return set_err(ctx, rc, gerr);
+    const Geometry& g = ctx->g;
+    const int cw = g.canvas_w(), ch = g.canvas_h();
+
+    CK(ctx, conv_kernels_init());
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    CK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->dbg_host), sizeof(DebugBlock), cudaHostAllocMapped));
+    std::memset(ctx->dbg_host, 0, sizeof(DebugBlock));
+    CK(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->dbg_dev), ctx->dbg_host, 0));
+
+    // geometry tables
+    std::vector<uint8_t> colflag(cw), rowflag(ch);
+    for (int i = 0; i < cw; ++i) colflag[i] = g.x.src[i] >= 0;
+    for (int i = 0; i < ch; ++i) rowflag[i] = g.y.src[i] >= 0;
+    if ((rc = upload(ctx, &ctx->d_colflag, colflag.data(), cw))) return rc;
+    if ((rc = upload(ctx, &ctx->d_rowflag, rowflag.data(), ch))) return rc;
+    if ((rc = upload(ctx, &ctx->d_srcx, g.x.src.data(), sizeof(int) * cw))) return rc;
+    if ((rc = upload(ctx, &ctx->d_srcy, g.y.src.data(), sizeof(int) * ch))) return rc;
+    if ((rc = upload(ctx, &ctx->d_outx, g.x.out.data(), sizeof(int) * cw))) return rc;
+    if ((rc = upload(ctx, &ctx->d_outy, g.y.out.data(), sizeof(int) * ch))) return rc;
+
+    // activation canvases (ping-pong), zero-initialised
+    ctx->act_bytes = static_cast<size_t>(cw) * ch * 64 * sizeof(__half);
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->act[i]), ctx->act_bytes);
+        if (e == cudaErrorMemoryAllocation) return set_err(ctx, REVE_E_NOMEM, "out of device memory for the activation canvas");
+        CK(ctx, e);
+        CK(ctx, cudaMemset(ctx->act[i], 0, ctx->act_bytes));
+    }
+
+    // tensor maps
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(ctx, REVE_E_CUDA, "driver does not export cuTensorMapEncodeTiled");
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = encode_map(ctx, enc, &ctx->map_in[i], ctx->act[i], cw, ch, kBoxPx))) return rc;
+        if ((rc = encode_map(ctx, enc, &ctx->map_out[i], ctx->act[i], cw, ch, kStripPx))) return rc;
+    }
+
+    // weights
+    const int tail_ng = m.scale == 2 ? 16 : (m.scale == 3 ? 32 : 48);
+    for (int k = 1; k < kNumConv; ++k) {
+        const int ng = (k == kNumConv - 1) ? tail_ng : 64;
+        std::vector<uint16_t> blob(conv_weight_blob_bytes(ng) / 2);
+        pack_conv_weights(m.conv[k].w.data(), m.conv[k].out_ch, ng, blob.data());
+        if ((rc = upload(ctx, &ctx->d_wblob[k], blob.data(), blob.size() * 2))) return rc;
+    }
+
+    // parameter blocks
+    Conv0Params& c0 = ctx->c0;
+    std::memset(&c0, 0, sizeof c0);
+    c0.canvas_w = cw;
+    c0.canvas_h = ch;
+    c0.src_x = ctx->d_srcx;
+    c0.src_y = ctx->d_srcy;
+    c0.dst = ctx->act[0];
+    for (int co = 0; co < 64; ++co) {
+        for (int c = 0; c < 3; ++c)
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx)
+                    c0.w[(ky * 3 + kx) * 3 + c][co] = m.conv[0].w[((static_cast<size_t>(co) * 3 + c) * 3 + ky) * 3 + kx];
+        c0.bias[co] = m.conv[0].b[co];
+        c0.slope[co] = m.conv[0].slope[co];
+    }
+    const int n_strips = (cw + kStripPx - 1) / kStripPx;
+    const long long total = static_cast<long long>(n_strips) * ch;
+    ctx->grid = static_cast<int>(total < ctx->sm_count ? total : ctx->sm_count);
+    // Debug knob (tests only): cap the persistent grid so one CTA walks many rows / strips.
+    if (const char* ge = std::getenv("REVE_DEBUG_GRID")) {
+        const int gcap = std::atoi(ge);
+        if (gcap >= 1 && gcap < ctx->grid) ctx->grid = gcap;
+    }
+    for (int k = 0; k <= kNumBody; ++k) {
+        ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
+        std::memset(&p, 0, sizeof p);
+        p.canvas_w = cw;
+        p.canvas_h = ch;
+        p.n_strips = n_strips;
+        p.total_rows = static_cast<int>(total);
+        p.colflag = ctx->d_colflag;
+        p.rowflag = ctx->d_rowflag;
+        p.weights = ctx->d_wblob[k + 1];
+        p.dbg = ctx->dbg_dev;
+        p.src_x = ctx->d_srcx;
+        p.src_y = ctx->d_srcy;
+        p.out_x = ctx->d_outx;
+        p.out_y = ctx->d_outy;
+        const ConvLayer& L = m.conv[k + 1];
+        for (int c = 0; c < L.out_ch; ++c) {
+            p.bias[c] = L.b[c];
+            p.slope[c] = L.slope.empty() ? 0.f : L.slope[c];
+        }
+    }
+
+    // staging ring
+    ctx->ring.resize(ring_depth);
+    const size_t in_bytes = static_cast<size_t>(in_w) * in_h * 3;
+    const size_t out_bytes = in_bytes * m.scale * m.scale;
+    for (auto& s : ctx->ring) {
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&s.d_in), in_bytes));
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&s.d_out), out_bytes));
+        CK(ctx, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    return REVE_OK;
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" {
+
+int reve_version(void) { return REVE_VERSION; }
+
+const char* reve_strerror(int status) {
+    switch (status) {
+        case REVE_OK: return "ok";
+        case REVE_E_INVAL: return "invalid argument";
+        case REVE_E_NOMEM: return "out of memory";
+        case REVE_E_CUDA: return "CUDA error";
+        case REVE_E_IO: return "I/O error";
+        case REVE_E_MODEL: return "not a realesr-animevideov3 model";
+        case REVE_E_ARCH: return "device is not sm_100";
+        case REVE_E_BUSY: return "submit ring full";
+        case REVE_E_EMPTY: return "nothing in flight";
+        default: return "unknown status";
+    }
+}
+
+const char* reve_last_error(const reve_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int reve_device_count(int* n) {
+    if (!n) return set_err(nullptr, REVE_E_INVAL, "n is NULL");
+    *n = 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "cudaGetDeviceCount", e));
+    for (int d = 0; d < ndev; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++*n;
+    }
+    return REVE_OK;
+}
+
+int reve_model_load_ncnn(const char* param_path, const char* bin_path, reve_model** out) {
+    if (!param_path || !bin_path || !out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    *out = nullptr;
+    reve_model* m = new (std::nothrow) reve_model();
+    if (!m) return set_err(nullptr, REVE_E_NOMEM, "out of host memory");
+    std::string err;
+    int rc;
+    try {
+        rc = model_load_ncnn(param_path, bin_path, m->m, err);
+    } catch (const std::exception& e) {
+        rc = REVE_E_NOMEM;
+        err = e.what();
+    }
+    if (rc != REVE_OK) {
+        delete m;
+        return set_err(nullptr, rc, err);
+    }
+    *out = m;
+    return REVE_OK;
+}
+
+int reve_model_random(int scale, uint64_t seed, reve_model** out) {
+    if (!out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    *out = nullptr;
+    reve_model* m = new (std::nothrow) reve_model();
+    if (!m) return set_err(nullptr, REVE_E_NOMEM, "out of host memory");
+    std::string err;
+    int rc;
+    try {
+        rc = model_random(scale, seed, m->m, err);
+    } catch (const std::exception& e) {
+        rc = REVE_E_NOMEM;
+        err = e.what();
+    }
+    if (rc != REVE_OK) {
+        delete m;
+        return set_err(nullptr, rc, err);
+    }
+    *out = m;
+    return REVE_OK;
+}
+
+int reve_model_save_ncnn(const reve_model* m, const char* param_path, const char* bin_path, int fp16) {
+    if (!m || !param_path || !bin_path) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    std::string err;
+    int rc;
+    try {
+        rc = model_save_ncnn(m->m, param_path, bin_path, fp16 != 0, err);
+    } catch (const std::exception& e) {
+        rc = REVE_E_NOMEM;
+        err = e.what();
+    }
+    return rc == REVE_OK ? rc : set_err(nullptr, rc, err);
+}
+
+int reve_model_info(const reve_model* m, int* scale, int* num_feat, int* num_conv) {
+    if (!m) return set_err(nullptr, REVE_E_INVAL, "model is NULL");
+    if (scale) *scale = m->m.scale;
+    if (num_feat) *num_feat = kNumFeat;
+    if (num_conv) *num_conv = kNumBody;
+    return REVE_OK;
+}
+
+void reve_model_free(reve_model* m) { delete m; }
+
+int reve_ctx_create(int device, const reve_model* m, int in_w, int in_h, int tile, int prepad, int ring_depth,
+                    reve_ctx** out) {
+    if (!out) return set_err(nullptr, REVE_E_INVAL, "out is NULL");
+    *out = nullptr;
+    if (!m) return set_err(nullptr, REVE_E_INVAL, "model is NULL");
+    if (ring_depth < 1 || ring_depth > 16) return set_err(nullptr, REVE_E_INVAL, "ring_depth must be within 1..16");
+    reve_ctx* ctx = new (std::nothrow) reve_ctx();
+    if (!ctx) return set_err(nullptr, REVE_E_NOMEM, "out of host memory");
+    int rc;
+    try {
+        rc = create_ctx(ctx, device, m->m, in_w, in_h, tile, prepad, ring_depth);
+    } catch (const std::exception& e) {
+        rc = set_err(ctx, REVE_E_NOMEM, e.what());
+    }
+    if (rc != REVE_OK) {
+        g_last_error = ctx->err;
+        destroy_ctx(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return REVE_OK;
+}
+
+void reve_ctx_destroy(reve_ctx* ctx) { destroy_ctx(ctx); }
+
+int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    if (in_w) *in_w = ctx->g.in_w;
+    if (in_h) *in_h = ctx->g.in_h;
+    if (out_w) *out_w = ctx->g.in_w * ctx->scale;
+    if (out_h) *out_h = ctx->g.in_h * ctx->scale;
+    if (scale) *scale = ctx->scale;
+    return REVE_OK;
+}
+
+int reve_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return set_err(nullptr, REVE_E_INVAL, "bad argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation) return set_err(nullptr, REVE_E_NOMEM, "pinned allocation failed");
+    if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "cudaHostAlloc", e));
+    return REVE_OK;
+}
+
+void reve_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int reve_submit(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, uint8_t* rgb_out, size_t out_stride,
+                uint64_t tag) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    if (!rgb_in || !rgb_out) return set_err(ctx, REVE_E_INVAL, "frame pointer is NULL");
+    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3, out_row = in_row * ctx->scale;
+    if (in_stride < in_row || out_stride < out_row) return set_err(ctx, REVE_E_INVAL, "row stride smaller than the row");
+    if (ctx->inflight == static_cast<int>(ctx->ring.size())) return set_err(ctx, REVE_E_BUSY, "submit ring full: call reve_wait");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->ring[ctx->head];
+    const int in_h = ctx->g.in_h, out_h = in_h * ctx->scale;
+    CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, in_h, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_comp, s.ev_h2d, 0));
+    int rc = enqueue_frame(ctx, s.d_in, static_cast<long long>(in_row), s.d_out, static_cast<long long>(out_row));
+    if (rc != REVE_OK) return rc;
+    CK(ctx, cudaEventRecord(s.ev_comp, ctx->s_comp));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_comp, 0));
+    CK(ctx, cudaMemcpy2DAsync(rgb_out, out_stride, s.d_out, out_row, out_row, out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(ctx, cudaEventRecord(s.ev_done, ctx->s_d2h));
+    s.tag = tag;
+    ctx->head = (ctx->head + 1) % static_cast<int>(ctx->ring.size());
+    ctx->inflight++;
+    return REVE_OK;
+}
+
+int reve_wait(reve_ctx* ctx, uint64_t* tag) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    if (ctx->inflight == 0) return set_err(ctx, REVE_E_EMPTY, "nothing in flight");
+    Slot& s = ctx->ring[ctx->oldest];
+    ctx->oldest = (ctx->oldest + 1) % static_cast<int>(ctx->ring.size());
+    ctx->inflight--;
+    if (tag) *tag = s.tag;
+    CK(ctx, cudaEventSynchronize(s.ev_done));
+    return REVE_OK;
+}
+
+int reve_sync(reve_ctx* ctx) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    return REVE_OK;
+}
+
+int reve_upscale_device(reve_ctx* ctx, const void* d_in, void* d_out, int n_frames) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    if (!d_in || !d_out || n_frames < 0) return set_err(ctx, REVE_E_INVAL, "bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3, out_row = in_row * ctx->scale;
+    const size_t in_bytes = in_row * ctx->g.in_h, out_bytes = out_row * ctx->g.in_h * ctx->scale;
+    for (int f = 0; f < n_frames; ++f) {
+        int rc = enqueue_frame(ctx, static_cast<const uint8_t*>(d_in) + f * in_bytes, static_cast<long long>(in_row),
+                               static_cast<uint8_t*>(d_out) + f * out_bytes, static_cast<long long>(out_row));
+        if (rc != REVE_OK) return rc;
+    }
+    return REVE_OK;
+}
+
+int reve_ctx_stream(const reve_ctx* ctx, void** stream) {
+    if (!ctx || !stream) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    *stream = ctx->s_comp;
+    return REVE_OK;
+}
+
+int reve_ctx_set_profiling(reve_ctx* ctx, int on) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    int rc = collect_profile(ctx);
+    ctx->profiling = on != 0;
+    return rc;
+}
+
+int reve_ctx_get_profile(reve_ctx* ctx, reve_profile* out, int reset) {
+    if (!ctx || !out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    int rc = collect_profile(ctx);
+    if (rc != REVE_OK) return rc;
+    *out = ctx->prof;
+    if (reset) ctx->prof = reve_profile{};
+    return REVE_OK;
+}
+
+int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, int layer, float* out,
+                        size_t cap_floats, int* canvas_w, int* canvas_h) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    const int cw = ctx->g.canvas_w(), ch = ctx->g.canvas_h();
+    if (canvas_w) *canvas_w = cw;
+    if (canvas_h) *canvas_h = ch;
+    if (!rgb_in || !out || layer < 1 || layer > kNumBody + 1) return set_err(ctx, REVE_E_INVAL, "bad argument");
+    const size_t n = static_cast<size_t>(cw) * ch * 64;
+    if (cap_floats < n) return set_err(ctx, REVE_E_INVAL, "output buffer too small");
+    if (ctx->inflight) return set_err(ctx, REVE_E_BUSY, "frames in flight");
+    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3;
+    if (in_stride < in_row) return set_err(ctx, REVE_E_INVAL, "row stride smaller than the row");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->ring[0];
+    CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, ctx->g.in_h, cudaMemcpyHostToDevice, ctx->s_comp));
+    int rc = enqueue_frame(ctx, s.d_in, static_cast<long long>(in_row), s.d_out, static_cast<long long>(in_row) * ctx->scale, layer);
+    if (rc != REVE_OK) return rc;
+    std::vector<__half> h(n);
+    CK(ctx, cudaMemcpyAsync(h.data(), ctx->act[(layer - 1) & 1], n * sizeof(__half), cudaMemcpyDeviceToHost, ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    for (size_t i = 0; i < n; ++i) {
+        uint16_t bits;
+        std::memcpy(&bits, &h[i], 2);
+        out[i] = f16_to_f32(bits);
+    }
+    return REVE_OK;
+}
+
+int reve_geometry(int in_w, int in_h, int scale, int tile, int prepad, int* canvas_w, int* canvas_h, int* src_x,
+                  int* out_x, int* src_y, int* out_y, size_t cap) {
+    Geometry g;
+    std::string err;
+    int rc;
+    try {
+        rc = make_geometry(in_w, in_h, scale, tile, prepad, g, err);
+    } catch (const std::exception& e) {
+        rc = REVE_E_NOMEM;
+        err = e.what();
+    }
+    if (rc != REVE_OK) return set_err(nullptr, rc, err);
+    if (canvas_w) *canvas_w = g.canvas_w();
+    if (canvas_h) *canvas_h = g.canvas_h();
+    if ((src_x || out_x) && cap < static_cast<size_t>(g.canvas_w())) return set_err(nullptr, REVE_E_INVAL, "cap too small");
+    if ((src_y || out_y) && cap < static_cast<size_t>(g.canvas_h())) return set_err(nullptr, REVE_E_INVAL, "cap too small");
+    for (int i = 0; i < g.canvas_w(); ++i) {
+        if (src_x) src_x[i] = g.x.src[i];
+        if (out_x) out_x[i] = g.x.out[i];
+    }
+    for (int i = 0; i < g.canvas_h(); ++i) {
+        if (src_y) src_y[i] = g.y.src[i];
+        if (out_y) out_y[i] = g.y.out[i];
+    }
+    return REVE_OK;
+}
+
+}  // extern "C"

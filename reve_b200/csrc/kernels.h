@@ -1,0 +1,64 @@
+// Kernel-side parameter blocks and launchers (internal to libreve_cuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace reve {
+
+constexpr int kBoxPx = 128;    // pixels per TMA row box = UMMA M
+constexpr int kStripPx = 126;  // valid output pixels per strip row (box minus the 2 halo columns)
+constexpr int kStages = 6;     // A-row ring depth
+constexpr int kConvThreads = 192;
+
+// Parameters of the tcgen05 3x3 convolution kernels (body: 64->64 + PReLU -> fp16 canvas;
+// tail: 64->3*s*s + PixelShuffle + nearest residual + u8 pack).  Passed as a __grid_constant__
+// so bias/slope are read straight from the constant bank.
+struct ConvParams {
+    int canvas_w, canvas_h;
+    int n_strips;
+    int total_rows;             // n_strips * canvas_h  (strip-rows of work)
+    const uint8_t* colflag;     // [canvas_w] 1 = pixel of a tile, 0 = gap column
+    const uint8_t* rowflag;     // [canvas_h]
+    const void* weights;        // pre-swizzled B operand blob of this layer (global memory)
+    DebugBlock* dbg;            // mapped pinned host memory, may be null
+    // tail only
+    const uint8_t* src;         // u8 RGB input frame (device)
+    uint8_t* dst;               // u8 RGB output frame (device)
+    long long src_stride, dst_stride;
+    const int* src_x;           // [canvas_w] source column (or -1)
+    const int* src_y;           // [canvas_h]
+    const int* out_x;           // [canvas_w] output column at input resolution (or -1)
+    const int* out_y;           // [canvas_h]
+    float bias[64];
+    float slope[64];
+};
+
+// First convolution (3 -> 64) + PReLU on CUDA cores, fused with the u8 -> float unpack, the
+// reflect-101 pre-pad gather and the canvas layout; weights live in the constant bank.
+struct Conv0Params {
+    int canvas_w, canvas_h;
+    const uint8_t* src;
+    long long src_stride;
+    const int* src_x;
+    const int* src_y;
+    __half* dst;               // canvas [canvas_h][canvas_w][64] fp16
+    float w[27][64];           // [(ky*3 + kx)*3 + c][co]
+    float bias[64];
+    float slope[64];
+};
+
+size_t conv_smem_bytes(int ng, bool tail);
+size_t conv_weight_blob_bytes(int ng);
+// Packs OIHW fp32 weights [co][64][3][3] into the pre-swizzled fp16 B-operand blob for group
+// width `ng` (co <= ng; missing output channels are zero).
+void pack_conv_weights(const float* w_oihw, int co, int ng, uint16_t* blob);
+
+cudaError_t conv_kernels_init();  // opt-in shared memory attributes; call once per device
+cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
+cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p);
+cudaError_t launch_conv0(cudaStream_t st, const Conv0Params& p);
+
+}  // namespace reve

@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's upscale stage over the C ABI.
+
+``Upscaler`` is one ``reve_ctx`` (one GPU); ``upscale_segment`` mirrors
+``Video::upscale_segment`` (reference reve-shared/src/lib.rs:129-155): a directory of decoded
+frames in, the same file names upscaled out, one ``"<in> -> <out> done"`` line per frame on the
+progress stream (what reve-cli/src/main.rs:265-273 counts).  Every computation happens in
+libreve_cuda.so; nothing here computes pixels on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+REVE_E_BUSY = -7
+
+
+class ReveError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"[reve status {status}] {msg}")
+        self.status = status
+
+
+def load_library():
+    return _lib.load()
+
+
+def library_path() -> str:
+    return _lib.LIB_PATH
+
+
+def _check(rc: int, ctx=None):
+    if rc != 0:
+        lib = _lib.load()
+        msg = lib.reve_last_error(ctx).decode("utf-8", "replace")
+        if not msg:
+            msg = lib.reve_strerror(rc).decode()
+        raise ReveError(rc, msg)
+
+
+class Model:
+    """Weights of realesr-animevideov3-x{2,3,4} (replaces ``-n <name>`` + ``models\\``)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def load_ncnn(cls, param_path: str, bin_path: str) -> "Model":
+        h = C.c_void_p()
+        _check(_lib.load().reve_model_load_ncnn(param_path.encode(), bin_path.encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def random(cls, scale: int, seed: int) -> "Model":
+        h = C.c_void_p()
+        _check(_lib.load().reve_model_random(scale, seed, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def for_scale(cls, scale: int, model_dir: str = "models", seed: int = 0) -> "Model":
+        """The model the reference's CLI intends for ``-s scale``:
+        ``<model_dir>/realesr-animevideov3-x{scale}.param|.bin`` if present, otherwise the seeded
+        random init of the same architecture (the weight files are not available offline)."""
+        base = os.path.join(model_dir, f"realesr-animevideov3-x{scale}")
+        if os.path.exists(base + ".param") and os.path.exists(base + ".bin"):
+            return cls.load_ncnn(base + ".param", base + ".bin")
+        return cls.random(scale, seed)
+
+    def save_ncnn(self, param_path: str, bin_path: str, fp16: bool = True) -> None:
+        _check(_lib.load().reve_model_save_ncnn(self._h, param_path.encode(), bin_path.encode(), int(fp16)))
+
+    @property
+    def scale(self) -> int:
+        s = C.c_int()
+        _check(_lib.load().reve_model_info(self._h, C.byref(s), None, None))
+        return s.value
+
+    def close(self):
+        if self._h:
+            _lib.load().reve_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def geometry(in_w: int, in_h: int, scale: int, tile: int, prepad: int):
+    """Canvas tables (host only): (canvas_w, canvas_h, src_x, out_x, src_y, out_y)."""
+    lib = _lib.load()
+    cw, ch = C.c_int(), C.c_int()
+    _check(lib.reve_geometry(in_w, in_h, scale, tile, prepad, C.byref(cw), C.byref(ch), None, None, None, None, 0))
+    n = max(cw.value, ch.value)
+    arrs = [np.zeros(n, np.int32) for _ in range(4)]
+    _check(lib.reve_geometry(in_w, in_h, scale, tile, prepad, C.byref(cw), C.byref(ch),
+                             *[a.ctypes.data for a in arrs], n))
+    return (cw.value, ch.value, arrs[0][:cw.value].copy(), arrs[1][:cw.value].copy(),
+            arrs[2][:ch.value].copy(), arrs[3][:ch.value].copy())
+
+
+class Upscaler:
+    """One GPU context for a fixed input frame size.  tile=200, prepad=10 are the values the
+    reference's spawned upscaler uses; tile=0 is the whole-frame variant."""
+
+    def __init__(self, model: Model, in_w: int, in_h: int, tile: int = 200, prepad: int = 10,
+                 device: int = 0, ring_depth: int = 3):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.model = model
+        _check(self._lib.reve_ctx_create(device, model._h, in_w, in_h, tile, prepad, ring_depth, C.byref(self._h)))
+        v = [C.c_int() for _ in range(5)]
+        _check(self._lib.reve_ctx_info(self._h, *[C.byref(x) for x in v]), self._h)
+        self.in_w, self.in_h, self.out_w, self.out_h, self.scale = (x.value for x in v)
+        self.ring_depth = ring_depth
+        self.device = device
+        self._pinned: List[int] = []
+
+    # -- pinned host buffers ----------------------------------------------------------------
+    def pinned(self, shape: Sequence[int]) -> np.ndarray:
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        _check(self._lib.reve_host_alloc(n, C.byref(p)))
+        self._pinned.append(p.value)
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(shape)
+
+    # -- frame API ----------------------------------------------------------------------------
+    def submit(self, frame: np.ndarray, out: np.ndarray, tag: int = 0) -> None:
+        if frame.dtype != np.uint8 or frame.shape != (self.in_h, self.in_w, 3):
+            raise ValueError(f"frame must be u8 [{self.in_h},{self.in_w},3]")
+        if out.dtype != np.uint8 or out.shape != (self.out_h, self.out_w, 3):
+            raise ValueError(f"out must be u8 [{self.out_h},{self.out_w},3]")
+        if frame.strides[1:] != (3, 1) or out.strides[1:] != (3, 1):
+            raise ValueError("pixels must be packed RGB")
+        _check(self._lib.reve_submit(self._h, frame.ctypes.data, frame.strides[0], out.ctypes.data,
+                                     out.strides[0], tag), self._h)
+
+    def wait(self) -> int:
+        tag = C.c_uint64()
+        _check(self._lib.reve_wait(self._h, C.byref(tag)), self._h)
+        return tag.value
+
+    def sync(self) -> None:
+        _check(self._lib.reve_sync(self._h), self._h)
+
+    def upscale(self, frame: np.ndarray) -> np.ndarray:
+        """Synchronous single frame (tests)."""
+        frame = np.ascontiguousarray(frame)
+        out = np.empty((self.out_h, self.out_w, 3), np.uint8)
+        self.submit(frame, out, 0)
+        self.wait()
+        return out
+
+    def upscale_many(self, frames: Iterable[np.ndarray], outs: Iterable[np.ndarray],
+                     on_done: Optional[Callable[[int], None]] = None) -> int:
+        """Pipelined: keeps up to ring_depth frames in flight (H2D / compute / D2H overlapped)."""
+        inflight = 0
+        n = 0
+        for i, (f, o) in enumerate(zip(frames, outs)):
+            if inflight == self.ring_depth:
+                t = self.wait()
+                inflight -= 1
+                if on_done:
+                    on_done(t)
+            self.submit(f, o, i)
+            inflight += 1
+            n += 1
+        while inflight:
+            t = self.wait()
+            inflight -= 1
+            if on_done:
+                on_done(t)
+        return n
+
+    def upscale_device(self, d_in_ptr: int, d_out_ptr: int, n_frames: int) -> None:
+        _check(self._lib.reve_upscale_device(self._h, d_in_ptr, d_out_ptr, n_frames), self._h)
+
+    @property
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _check(self._lib.reve_ctx_stream(self._h, C.byref(s)), self._h)
+        return s.value or 0
+
+    def set_profiling(self, on: bool) -> None:
+        _check(self._lib.reve_ctx_set_profiling(self._h, int(on)), self._h)
+
+    def profile(self, reset: bool = True) -> dict:
+        p = _lib.reve_profile()
+        _check(self._lib.reve_ctx_get_profile(self._h, C.byref(p), int(reset)), self._h)
+        return {k: getattr(p, k) for k, _ in p._fields_}
+
+    def debug_features(self, frame: np.ndarray, layer: int) -> np.ndarray:
+        """fp16 feature canvas after `layer` conv+PReLU stages, as float32 [CH, CW, 64]."""
+        frame = np.ascontiguousarray(frame)
+        cw, ch = C.c_int(), C.c_int()
+        self._lib.reve_debug_features(self._h, None, 0, 0, None, 0, C.byref(cw), C.byref(ch))
+        out = np.empty((ch.value, cw.value, 64), np.float32)
+        _check(self._lib.reve_debug_features(self._h, frame.ctypes.data, frame.strides[0], layer,
+                                             out.ctypes.data, out.size, C.byref(cw), C.byref(ch)), self._h)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.reve_ctx_destroy(self._h)
+            self._h = None
+        for p in getattr(self, "_pinned", []):
+            self._lib.reve_host_free(p)
+        self._pinned = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------
+# Segment-level mirror of Video::upscale_segment
+# ----------------------------------------------------------------------------------------------
+def _read_frame(path: str) -> np.ndarray:
+    if path.endswith(".npy"):
+        return np.load(path)
+    import cv2  # host-side decode only (the reference decodes PNG on the host as well)
+    img = cv2.imread(path, cv2.IMREAD_COLOR)
+    if img is None:
+        raise IOError(f"cannot decode {path}")
+    return np.ascontiguousarray(img[:, :, ::-1])
+
+
+def _write_frame(path: str, rgb: np.ndarray) -> None:
+    if path.endswith(".npy"):
+        np.save(path, rgb)
+        return
+    import cv2
+    if not cv2.imwrite(path, np.ascontiguousarray(rgb[:, :, ::-1])):
+        raise IOError(f"cannot encode {path}")
+
+
+def upscale_segment(input_dir: str, output_dir: str, scale: int, model: Optional[Model] = None,
+                    tile: int = 200, prepad: int = 10, device: int = 0, fmt: str = "png",
+                    progress=None, model_dir: str = "models") -> int:
+    """Drop-in for the process spawned by Video::upscale_segment (reference
+    reve-shared/src/lib.rs:134-147: ``-i input_dir -o output_dir -n realesr-animevideov3-x2 -s
+    scale -f png -v``): every frame file of ``input_dir`` (sorted by name) is upscaled into
+    ``output_dir`` under the same stem with extension ``fmt``; with ``progress`` (a text stream)
+    one ``"<in> -> <out> done"`` line is written per finished frame, which is what
+    reve-cli/src/main.rs:265-273 counts.  Unlike the reference, failures raise instead of being
+    ignored.  Returns the number of frames written."""
+    names = sorted(n for n in os.listdir(input_dir)
+                   if n.lower().endswith((".png", ".jpg", ".jpeg", ".webp", ".npy")))
+    if not names:
+        return 0
+    os.makedirs(output_dir, exist_ok=True)
+    own_model = model is None
+    if own_model:
+        model = Model.for_scale(scale, model_dir)
+    if model.scale != scale:
+        raise ValueError(f"model is x{model.scale} but scale {scale} was requested")
+    first = _read_frame(os.path.join(input_dir, names[0]))
+    h, w = first.shape[:2]
+    up = Upscaler(model, w, h, tile=tile, prepad=prepad, device=device, ring_depth=3)
+    try:
+        ins = [up.pinned((h, w, 3)) for _ in range(up.ring_depth)]
+        outs = [up.pinned((up.out_h, up.out_w, 3)) for _ in range(up.ring_depth)]
+        pending: List[Tuple[int, str, str]] = []
+        done = 0
+
+        def retire():
+            nonlocal done
+            up.wait()
+            slot, src, dst = pending.pop(0)
+            _write_frame(dst, outs[slot])
+            done += 1
+            if progress is not None:
+                progress.write(f"{src} -> {dst} done\n")
+                progress.flush()
+
+        for i, name in enumerate(names):
+            slot = i % up.ring_depth
+            if len(pending) == up.ring_depth:
+                retire()
+            frame = first if i == 0 else _read_frame(os.path.join(input_dir, name))
+            if frame.shape != (h, w, 3):
+                raise ValueError(f"{name}: frame size differs from the first frame of the segment")
+            ins[slot][...] = frame
+            src = os.path.join(input_dir, name)
+            dst = os.path.join(output_dir, os.path.splitext(name)[0] + "." + fmt)
+            up.submit(ins[slot], outs[slot], i)
+            pending.append((slot, src, dst))
+        while pending:
+            retire()
+        return done
+    finally:
+        up.close()
+        if own_model:
+            model.close()

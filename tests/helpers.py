@@ -1,0 +1,56 @@
+"""Shared helpers for the parity tests (oracle side).  Test infrastructure only."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import srvgg  # noqa: E402
+
+
+def oracle_canvas(frame: np.ndarray, w: srvgg.Weights, tile: int, prepad: int, layer: int):
+    """Oracle feature map after `layer` conv+PReLU stages laid out on the device canvas:
+    float32 [CH, CW, 64], zeros at gap rows/columns.  Follows reve_b200/csrc/geometry.cpp's layout
+    (padded tiles side by side, one gap pixel between tiles)."""
+    h, wpx = frame.shape[:2]
+    t = tile if tile > 0 else max(h, wpx)
+    xs = list(range(0, wpx, t))
+    ys = list(range(0, h, t))
+    tws = [min(t, wpx - x0) for x0 in xs]
+    ths = [min(t, h - y0) for y0 in ys]
+    cw = sum(tw + 2 * prepad for tw in tws) + len(xs) - 1
+    ch = sum(th + 2 * prepad for th in ths) + len(ys) - 1
+    canvas = np.zeros((ch, cw, 64), np.float32)
+    cy = 0
+    for y0, th in zip(ys, ths):
+        cx = 0
+        for x0, tw in zip(xs, tws):
+            tl = srvgg.padded_tile(frame, x0, y0, tw, th, prepad)
+            x = (tl.astype(np.float32) * np.float32(1.0 / 255.0)).transpose(2, 0, 1)
+            _, feats, _ = srvgg.forward(x, w, taps=True)
+            f = feats[layer - 1]  # [64, ph, pw]
+            canvas[cy:cy + th + 2 * prepad, cx:cx + tw + 2 * prepad] = f.transpose(1, 2, 0)
+            cx += tw + 2 * prepad + 1
+        cy += th + 2 * prepad + 1
+    return canvas
+
+
+def feature_report(dev: np.ndarray, ref: np.ndarray) -> dict:
+    err = np.abs(dev - ref)
+    tol = 2e-2 + 2e-2 * np.abs(ref)
+    bad = err > tol
+    rep = {"max_err": float(err.max()), "mean_err": float(err.mean()), "bad_frac": float(bad.mean()),
+           "ref_absmax": float(np.abs(ref).max())}
+    if bad.any():
+        rows = np.where(bad.any(axis=(1, 2)))[0]
+        cols = np.where(bad.any(axis=(0, 2)))[0]
+        chans = np.where(bad.any(axis=(0, 1)))[0]
+        rep["bad_rows"] = f"{len(rows)} rows, first {rows[:12].tolist()} last {rows[-4:].tolist()}"
+        rep["bad_cols"] = f"{len(cols)} cols, first {cols[:12].tolist()} last {cols[-4:].tolist()}"
+        rep["bad_chans"] = f"{len(chans)} ch, first {chans[:12].tolist()}"
+    return rep
