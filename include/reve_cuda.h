@@ -119,6 +119,10 @@ int reve_ctx_get_profile(reve_ctx* ctx, reve_profile* out, int reset);
  * (cap_floats = capacity).  canvas_w/h may be NULL.  Used by the per-layer parity tests. */
 int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, int layer,
                         float* out, size_t cap_floats, int* canvas_w, int* canvas_h);
+/* Test hook: with REVE_DEBUG_TRACE=1 in the environment at context creation, CTA 0 of body layer 5
+ * records clock64() timestamps (MMA warp: out[4*i + 0..2] for input row i; epilogue group leaders:
+ * out[1024 + 4*t + 0..2] for output row t); this copies the first n (<= 2048) words out. */
+int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n);
 /* Canvas geometry tables (context-free, host only; test hook): the canvas is the side-by-side
  * layout of upstream's padded tiles.  For canvas column/row i: the source frame coordinate feeding
  * it (reflect-101 applied; -1 for a gap) and the output coordinate at input resolution (-1 if

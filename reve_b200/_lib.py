@@ -40,6 +40,7 @@ SIGNATURES = {
     "reve_ctx_get_profile": (C.c_int, [C.c_void_p, C.POINTER(reve_profile), C.c_int]),
     "reve_debug_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "reve_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "reve_geometry": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 2 + [C.c_void_p] * 4 + [C.c_size_t]),
 }
 

@@ -51,14 +51,15 @@ struct reve_ctx {
     size_t act_bytes = 0;
     uint8_t *d_colflag = nullptr, *d_rowflag = nullptr;
     int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr;
-    void* d_wblob[kNumConv] = {};
-    CUtensorMap map_in[2], map_out[2];
+    void* d_wblob[kNumConv] = {};  // per layer: forward-sweep blob followed by the reverse-sweep blob
+    CUtensorMap map_in[2];
     Conv0Params c0;
     ConvParams body[kNumBody];
     ConvParams tail;
     int grid = 0;
     DebugBlock* dbg_host = nullptr;
     DebugBlock* dbg_dev = nullptr;
+    long long* d_trace = nullptr;  // REVE_DEBUG_TRACE: timeline of CTA 0 of body layer 5
     std::vector<Slot> ring;
     int head = 0, oldest = 0, inflight = 0;
     bool profiling = false;
@@ -134,7 +135,7 @@ int enqueue_frame(reve_ctx* ctx, const uint8_t* d_in, long long in_stride, uint8
     ctx->prof.launches_conv0++;
     prof_mark(ctx, 0);
     for (int k = 0; k < kNumBody && k + 1 < stop_after_layers; ++k) {
-        CK(ctx, launch_conv_body(ctx->s_comp, ctx->grid, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], ctx->body[k]));
+        CK(ctx, launch_conv_body(ctx->s_comp, ctx->grid, ctx->map_in[k & 1], ctx->body[k]));
         ctx->prof.launches_body++;
         prof_mark(ctx, 1);
     }
@@ -190,6 +191,7 @@ void destroy_ctx(reve_ctx* ctx) {
     cudaFree(ctx->d_outx);
     cudaFree(ctx->d_outy);
     for (void* p : ctx->d_wblob) cudaFree(p);
+    cudaFree(ctx->d_trace);
     if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -251,15 +253,16 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
     for (int i = 0; i < 2; ++i) {
         if ((rc = encode_map(ctx, enc, &ctx->map_in[i], ctx->act[i], cw, ch, kBoxPx))) return rc;
-        if ((rc = encode_map(ctx, enc, &ctx->map_out[i], ctx->act[i], cw, ch, kStripPx))) return rc;
     }
 
     // weights
     const int tail_ng = m.scale == 2 ? 16 : (m.scale == 3 ? 32 : 48);
     for (int k = 1; k < kNumConv; ++k) {
         const int ng = (k == kNumConv - 1) ? tail_ng : 64;
-        std::vector<uint16_t> blob(conv_weight_blob_bytes(ng) / 2);
-        pack_conv_weights(m.conv[k].w.data(), m.conv[k].out_ch, ng, blob.data());
+        const size_t half = conv_weight_blob_bytes(ng) / 2;
+        std::vector<uint16_t> blob(2 * half);
+        pack_conv_weights(m.conv[k].w.data(), m.conv[k].out_ch, ng, false, blob.data());
+        pack_conv_weights(m.conv[k].w.data(), m.conv[k].out_ch, ng, true, blob.data() + half);
         if ((rc = upload(ctx, &ctx->d_wblob[k], blob.data(), blob.size() * 2))) return rc;
     }
 
@@ -287,16 +290,25 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         const int gcap = std::atoi(ge);
         if (gcap >= 1 && gcap < ctx->grid) ctx->grid = gcap;
     }
+    // Debug flags (tests / experiments): bit0 = never sweep in reverse, bit1 = no evict-first hint on
+    // activation loads, bit2 = evict-last hint on activation stores.
+    uint32_t dflags = 0;
+    if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) dflags = static_cast<uint32_t>(std::atoi(fe));
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         std::memset(&p, 0, sizeof p);
+        // conv0 writes the canvas top-down, so body layer 0 sweeps bottom-up, layer 1 top-down, ...
+        p.reverse = (dflags & 1u) ? 0 : ((k & 1) == 0);
+        p.flags = dflags;
+        p.out = (k < kNumBody) ? ctx->act[(k + 1) & 1] : nullptr;
         p.canvas_w = cw;
         p.canvas_h = ch;
         p.n_strips = n_strips;
         p.total_rows = static_cast<int>(total);
         p.colflag = ctx->d_colflag;
         p.rowflag = ctx->d_rowflag;
-        p.weights = ctx->d_wblob[k + 1];
+        p.weights = static_cast<const uint8_t*>(ctx->d_wblob[k + 1]) +
+                    (p.reverse ? conv_weight_blob_bytes(k < kNumBody ? 64 : tail_ng) : 0);
         p.dbg = ctx->dbg_dev;
         p.src_x = ctx->d_srcx;
         p.src_y = ctx->d_srcy;
@@ -307,6 +319,12 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             p.bias[c] = L.b[c];
             p.slope[c] = L.slope.empty() ? 0.f : L.slope[c];
         }
+    }
+
+    if (std::getenv("REVE_DEBUG_TRACE")) {
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_trace), 2048 * sizeof(long long)));
+        CK(ctx, cudaMemset(ctx->d_trace, 0, 2048 * sizeof(long long)));
+        ctx->body[5].trace = ctx->d_trace;
     }
 
     // staging ring
@@ -579,6 +597,14 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
         std::memcpy(&bits, &h[i], 2);
         out[i] = f16_to_f32(bits);
     }
+    return REVE_OK;
+}
+
+int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n) {
+    if (!ctx || !out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    if (!ctx->d_trace || n > 2048) return set_err(ctx, REVE_E_INVAL, "tracing is off (set REVE_DEBUG_TRACE=1) or n > 2048");
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    CK(ctx, cudaMemcpy(out, ctx->d_trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
     return REVE_OK;
 }
 

@@ -18,9 +18,12 @@
 //     strip and A is read from shared memory 12 times per row instead of 36.
 //   * A CTA owns a contiguous range of strip-rows (grid = #SMs, persistent), possibly spanning two
 //     strips; segments restart the 3-row window with their own halo rows.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/PReLU -> fp16 -> swizzled smem -> TMA store, or
-// for the tail: bias -> PixelShuffle + residual -> u8 -> global).
+//   * Alternate layers sweep their ranges in opposite directions (`reverse`): the rows a CTA wrote
+//     last in layer l are the rows it reads first in layer l+1, while they are still in L2.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warp-
+// uniform code, one elected lane issues), warps 2..9 = two epilogue groups that take alternate
+// output rows (TMEM -> registers -> bias/PReLU -> fp16 -> 256-bit global stores, or for the tail:
+// bias -> PixelShuffle + residual -> u8 -> global).
 #include "kernels.h"
 
 #include <algorithm>
@@ -33,7 +36,7 @@ namespace reve {
 namespace {
 
 constexpr int kRowBytes = kBoxPx * 128;  // 16 KB: 128 px * 64 ch * fp16
-constexpr int kCtrlBytes = 1024;
+constexpr int kCtrlBytes = 2048;
 constexpr int kGuard = 1024;
 
 __host__ __device__ constexpr int w_bytes(int ng) { return 3 * 3 * ng * 128; }
@@ -46,15 +49,21 @@ constexpr int kBarAEmpty = kBarAFull + 8 * kStages;
 constexpr int kBarAccFull = kBarAEmpty + 8 * kStages;
 constexpr int kBarAccEmpty = kBarAccFull + 8 * 8;
 constexpr int kTmemPtr = 512;
+constexpr int kOffBias = 1024;   // 64 floats
+constexpr int kOffSlope = 1280;  // 64 floats
 
 enum : uint32_t { TAG_W = 1, TAG_A_EMPTY = 2, TAG_A_FULL = 3, TAG_ACC_EMPTY = 4, TAG_ACC_FULL = 5 };
 
+// Range of (virtual) strip-rows of this CTA, cut into per-strip segments.  In reverse mode the
+// virtual index runs backwards over the physical one (strip' = n_strips-1-strip, y' = CH-1-y) and
+// the CTA takes the mirrored block, i.e. the same physical region as in forward mode.
 struct SegIter {
     long long lo, hi;
     int ch;
     __device__ SegIter(const ConvParams& p) : ch(p.canvas_h) {
-        lo = static_cast<long long>(blockIdx.x) * p.total_rows / gridDim.x;
-        hi = static_cast<long long>(blockIdx.x + 1) * p.total_rows / gridDim.x;
+        const unsigned b = p.reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+        lo = static_cast<long long>(b) * p.total_rows / gridDim.x;
+        hi = static_cast<long long>(b + 1) * p.total_rows / gridDim.x;
     }
     __device__ bool next(int& strip, int& ya, int& yb) {
         if (lo >= hi) return false;
@@ -67,27 +76,21 @@ struct SegIter {
     }
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t lo) {
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 
 template <int NG, bool TAIL>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
-                    const __grid_constant__ CUtensorMap out_map,
-                    const __grid_constant__ ConvParams p) {
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ ConvParams p) {
     constexpr int kWBytes = w_bytes(NG);
     constexpr int kTmemCols = tmem_cols(NG);
     constexpr int kOffW = kCtrlBytes;
     constexpr int kOffRing = kOffW + kWBytes + kGuard;
-    constexpr int kOffStage = kOffRing + kStages * kRowBytes + kGuard;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -106,7 +109,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
         }
         for (int s = 0; s < 8; ++s) {
             mbar_init(base + kBarAccFull + 8 * s, 1);
-            mbar_init(base + kBarAccEmpty + 8 * s, 128);
+            mbar_init(base + kBarAccEmpty + 8 * s, 4);  // one arrive per warp of the draining group
         }
         fence_mbar_init();
     }
@@ -114,9 +117,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
         tmem_alloc(base + kTmemPtr, kTmemCols);
         tmem_relinquish();
     }
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&in_map);
-        if (!TAIL) prefetch_tmap(&out_map);
+    if (warp == 0 && lane == 0) prefetch_tmap(&in_map);
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        // bias / PReLU slopes: shared-memory copies, read back as broadcast LDS.128 in the epilogue
+        // (constant-bank operands turn into long-latency LDCU loads on sm_100)
+        reinterpret_cast<float*>(base_ptr + kOffBias)[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+        reinterpret_cast<float*>(base_ptr + kOffSlope)[threadIdx.x - 64] = p.slope[threadIdx.x - 64];
     }
     tc_fence_before();
     __syncthreads();
@@ -124,112 +130,199 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kTmemPtr);
 
     const int CH = p.canvas_h;
+    const bool rev = p.reverse != 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             mbar_arrive_expect_tx(base + kBarW, kWBytes);
             bulk_load_1d(base + kOffW, p.weights, kWBytes, base + kBarW);
+            const uint64_t policy = (p.flags & 2u) ? kPolicyEvictNormal : kPolicyEvictFirst;
             SegIter it(p);
             int strip, ya, yb;
             uint32_t i = 0;
             while (it.next(strip, ya, yb)) {
-                const int x0 = strip * kStripPx;
+                const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
                 const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
                 for (int y = y_lo; y <= y_hi; ++y, ++i) {
-                    const uint32_t stage = i % kStages, use = i / kStages;
+                    const uint32_t stage = i & (kStages - 1), use = i / kStages;
                     mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                    if (p.flags & 32u) {  // timing experiment: no TMA traffic
+                        mbar_arrive(base + kBarAFull + 8 * stage);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
-                    tma_load_3d(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage,
-                                0, x0 - 1, y);
+                    tma_load_3d_hint(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage, 0,
+                                     x0 - 1, rev ? CH - 1 - y : y, policy);
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            mbar_wait(base + kBarW, 0, dbg, TAG_W);
-            tc_fence_after();
-            const uint32_t idesc1 = umma_idesc_f16(128, NG);
-            const uint32_t idesc2 = umma_idesc_f16(128, 2 * NG);
-            const uint32_t idesc3 = umma_idesc_f16(128, 3 * NG);
-            const uint32_t w_addr = base + kOffW;
-            SegIter it(p);
-            int strip, ya, yb;
-            uint32_t i = 0;
-            int t_base = 0;
-            while (it.next(strip, ya, yb)) {
-                const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
-                for (int y = y_lo; y <= y_hi; ++y, ++i) {
-                    const uint32_t stage = i % kStages, use = i / kStages;
-                    // group g (0..2) = vertical tap ky = g: input row y feeds output row y + 1 - g
-                    const int g_lo = (y + 1 <= yb) ? 0 : ((y <= yb) ? 1 : 2);
-                    const int g_hi = (y - 1 >= ya) ? 2 : ((y >= ya) ? 1 : 0);
-                    // groups whose output row receives its first contribution from this input row
-                    const int fresh_hi = (y == 0) ? g_hi : ((g_lo == 0) ? 0 : g_lo - 1);
-                    const int t0 = t_base + (y + 1 - ya);  // sequence number of output row y+1
-                    const int s0 = (-t0) & 7;              // its TMEM slot; group g -> (s0 + g) & 7
-                    for (int g = g_lo; g <= fresh_hi; ++g) {
-                        const int tg = t0 - g;
-                        mbar_wait(base + kBarAccEmpty + 8 * ((s0 + g) & 7), ((tg >> 3) & 1) ^ 1, dbg,
-                                  TAG_ACC_EMPTY, tg);
+        // Warp-uniform control flow; one elected lane issues.  The issuing thread is the scarce
+        // resource (13+ MMAs, 2 waits and 2 commits per ~1150 tensor-pipe cycles), so interior rows
+        // take a straight-line path whose descriptors differ from per-row bases by constants only.
+        mbar_wait(base + kBarW, 0, dbg, TAG_W);
+        tc_fence_after();
+        const uint32_t idesc1 = umma_idesc_f16(128, NG);
+        const uint32_t idesc2 = umma_idesc_f16(128, 2 * NG);
+        const uint32_t idesc3 = umma_idesc_f16(128, 3 * NG);
+        const uint64_t proto = umma_desc_sw128(0, 0);
+        const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
+        const uint32_t lo_flags = static_cast<uint32_t>(proto);              // LBO field
+        const uint32_t w_lo = lo_flags | ((base + kOffW) >> 4);
+        const uint32_t ring_lo = lo_flags | ((base + kOffRing) >> 4);
+        constexpr uint32_t kG = NG * 8;        // one group of B rows, in 16-byte units
+        constexpr uint32_t kDx = 3 * NG * 8;   // one dx block of B
+        static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
+        SegIter it(p);
+        int strip, ya, yb;
+        uint32_t i = 0;
+        int t_base = 0;
+        bool prechecked = false;  // barriers of the current row were already observed during the previous row
+        while (it.next(strip, ya, yb)) {
+            const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
+            for (int y = y_lo; y <= y_hi; ++y, ++i) {
+                const uint32_t stage = i & (kStages - 1), use = i / kStages;
+                const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
+                const int t0 = t_base + (y + 1 - ya);  // sequence number of output row y+1
+                const int s0 = (-t0) & 7;              // its TMEM slot; group g -> (s0 + g) & 7
+                const uint32_t bar_full = base + kBarAFull + 8 * stage;
+                if (y > ya && y < yb) {
+                    // ---- interior row: groups 0..2 enabled, only group 0 fresh, row y-1 completes.
+                    // The tensor pipe's instruction queue is shallow, so every cycle this thread spends
+                    // not issuing is a bubble: the barrier checks for row y+1 are made in the middle
+                    // of row y, while MMAs are queued.
+                    long long* const tr = (p.trace && blockIdx.x == 0 && i < 256) ? p.trace + i * 4 : nullptr;
+                    if (tr && lane == 0) tr[0] = clock64();
+                    if (!prechecked) {
+                        const uint32_t bar_e = base + kBarAccEmpty + 8 * s0;
+                        const uint32_t par_e = ((t0 >> 3) & 1) ^ 1;
+                        const bool ok_e = mbar_try_wait(bar_e, par_e);
+                        const bool ok_f = mbar_try_wait(bar_full, use & 1);
+                        if (!ok_e) mbar_wait(bar_e, par_e, dbg, TAG_ACC_EMPTY, t0);
+                        if (!ok_f) mbar_wait(bar_full, use & 1, dbg, TAG_A_FULL, i);
+                        tc_fence_after();
                     }
-                    mbar_wait(base + kBarAFull + 8 * stage, use & 1, dbg, TAG_A_FULL, i);
-                    tc_fence_after();
-
-                    const uint32_t a_row = base + kOffRing + stage * kRowBytes;
-                    auto issue = [&](uint64_t adesc, uint32_t w_k, int ga, int gb, uint32_t acc) {
-                        if (ga > gb) return;
-                        const int sa = (s0 + ga) & 7;
-                        const int n = gb - ga + 1;
-                        const int n1 = min(n, 8 - sa);
-                        umma_f16(tmem_base + sa * NG, adesc, umma_desc_sw128(w_k + ga * NG * 128, 0),
-                                 n1 == 1 ? idesc1 : (n1 == 2 ? idesc2 : idesc3), acc);
-                        if (n1 < n) {
-                            const int n2 = n - n1;
-                            umma_f16(tmem_base, adesc, umma_desc_sw128(w_k + (ga + n1) * NG * 128, 0),
-                                     n2 == 1 ? idesc1 : idesc2, acc);
-                        }
-                    };
+                    if (tr && lane == 0) { tr[1] = clock64(); tr[3] = (prechecked ? 1 : 0) | (s0 << 4); }
+                    const uint64_t a0 = mk_desc(desc_hi, a_lo - 8);
+                    const uint32_t d = tmem_base + s0 * NG;
+                    // part 1: the first K-step (fresh group overwrites) and three more K-steps
+                    if (elect_one()) {
+                        if (s0 <= 5) {
+                            umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                            umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
+                            for (int dxk = 1; dxk < 4; ++dxk)
+                                umma_f16(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_lo + dxk * 2), idesc3, 1u);
+                        } else if (s0 == 6) {
+                            umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                            umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc1, 1u);
+                            umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + 2 * kG), idesc1, 1u);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t a_addr = a_row + (dx - 1) * 128 + k * 32;
-                            // Measured on B200 (profiles/r01_notes.md): the 128B-swizzle XOR is taken
-                            // from the absolute shared-memory address bits, so a start address shifted
-                            // by whole 128-byte rows needs base_offset = 0 (the "(addr >> 7) & 7"
-                            // formula of the PTX manual produces garbage here).
-                            const uint64_t adesc = umma_desc_sw128(a_addr, 0);
-                            const uint32_t w_k = w_addr + dx * (3 * NG * 128) + k * 32;
-                            if (dx == 0 && k == 0 && fresh_hi >= g_lo) {
-                                issue(adesc, w_k, g_lo, fresh_hi, 0u);
-                                issue(adesc, w_k, fresh_hi + 1, g_hi, 1u);
-                            } else {
-                                issue(adesc, w_k, g_lo, g_hi, 1u);
+                            for (int dxk = 1; dxk < 4; ++dxk) {
+                                const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
+                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc2, 1u);
+                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + 2 * kG), idesc1, 1u);
+                            }
+                        } else {
+                            umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                            umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
+#pragma unroll
+                            for (int dxk = 1; dxk < 4; ++dxk) {
+                                const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
+                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc1, 1u);
+                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + kG), idesc2, 1u);
                             }
                         }
                     }
+                    // look ahead: are the barriers of row y+1 (if it is interior too) already complete?
+                    prechecked = false;
+                    if (y + 1 < yb) {
+                        const uint32_t nstage = (i + 1) & (kStages - 1);
+                        const bool ok_e = mbar_try_wait(base + kBarAccEmpty + 8 * ((s0 + 7) & 7), (((t0 + 1) >> 3) & 1) ^ 1);
+                        const bool ok_f = mbar_try_wait(base + kBarAFull + 8 * nstage, ((i + 1) / kStages) & 1);
+                        if (ok_e && ok_f) {
+                            tc_fence_after();
+                            prechecked = true;
+                        }
+                    }
+                    // part 2: the remaining eight K-steps, then the commits
+                    if (elect_one()) {
+                        if (s0 <= 5) {
+#pragma unroll
+                            for (int dxk = 4; dxk < 12; ++dxk) {
+                                const int dx = dxk >> 2, k = dxk & 3;
+                                umma_f16(d, mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2),
+                                         mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc3, 1u);
+                            }
+                        } else if (s0 == 6) {
+#pragma unroll
+                            for (int dxk = 4; dxk < 12; ++dxk) {
+                                const int dx = dxk >> 2, k = dxk & 3;
+                                const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
+                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int dxk = 4; dxk < 12; ++dxk) {
+                                const int dx = dxk >> 2, k = dxk & 3;
+                                const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
+                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
+                            }
+                        }
+                        umma_commit(base + kBarAEmpty + 8 * stage);
+                        umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));
+                    }
+                    __syncwarp();
+                    if (tr && lane == 0) tr[2] = clock64();
+                    continue;
+                }
+                prechecked = false;
+                // ---- edge rows of a segment (generic path)
+                // group g (0..2) = vertical tap: input row y feeds output row y + 1 - g
+                const int g_lo = (y + 1 <= yb) ? 0 : ((y <= yb) ? 1 : 2);
+                const int g_hi = (y - 1 >= ya) ? 2 : ((y >= ya) ? 1 : 0);
+                // groups whose output row receives its first contribution from this input row
+                const int fresh_hi = (y == 0) ? g_hi : ((g_lo == 0) ? 0 : g_lo - 1);
+                for (int g = g_lo; g <= fresh_hi; ++g) {
+                    const int tg = t0 - g;
+                    mbar_wait(base + kBarAccEmpty + 8 * ((s0 + g) & 7), ((tg >> 3) & 1) ^ 1, dbg, TAG_ACC_EMPTY, tg);
+                }
+                mbar_wait(bar_full, use & 1, dbg, TAG_A_FULL, i);
+                tc_fence_after();
+                if (elect_one()) {
+                    // one MMA per group and K-step: simple, and these rows are rare
+                    for (int dxk = 0; dxk < 12; ++dxk) {
+                        const int dx = dxk >> 2, k = dxk & 3;
+                        const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                        for (int g = g_lo; g <= g_hi; ++g)
+                            umma_f16(tmem_base + ((s0 + g) & 7) * NG, ad,
+                                     mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + g * kG), idesc1,
+                                     (dxk == 0 && g <= fresh_hi) ? 0u : 1u);
+                    }
                     umma_commit(base + kBarAEmpty + 8 * stage);  // A slot reusable once these MMAs retire
-                    if (g_hi == 2) umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));  // row y-1 done
-                    if (y == CH - 1 && yb == CH - 1)                                       // bottom edge: row y done too
+                    if (g_hi == 2) umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));  // row y-1 complete
+                    if (y == CH - 1 && yb == CH - 1)                                       // bottom edge: row y too
                         umma_commit(base + kBarAccFull + 8 * ((s0 + 1) & 7));
                 }
-                t_base += yb - ya + 1;
+                __syncwarp();
             }
+            t_base += yb - ya + 1;
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
+        const int grp = (warp - 2) >> 2;   // group 0 / 1 take even / odd output-row sequence numbers
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;       // M row = pixel index inside the 128-px box
-        const bool leader = (threadIdx.x == 64);
         const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         SegIter it(p);
         int strip, ya, yb;
         int t = 0;
-        uint32_t rowc = 0;
         while (it.next(strip, ya, yb)) {
-            const int x0 = strip * kStripPx;
+            const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
             const int cx = x0 - 1 + m;
             const bool inside = (m >= 1) && (m <= kStripPx) && (cx < p.canvas_w);
             const bool colok = inside && (p.colflag[cx] != 0);
@@ -239,54 +332,67 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
                 sx = p.src_x[cx];
             }
             for (int r = ya; r <= yb; ++r, ++t) {
+                if ((t & 1) != grp) continue;
+                const int pr = rev ? CH - 1 - r : r;  // physical canvas row
                 const int s = (-t) & 7;
+                long long* const tr = (p.trace && blockIdx.x == 0 && t < 256 && q == 0 && lane == 0)
+                                          ? p.trace + 1024 + t * 4 : nullptr;
+                if (tr) tr[0] = clock64();
                 mbar_wait(base + kBarAccFull + 8 * s, (t >> 3) & 1, dbg, TAG_ACC_FULL, t);
+                if (tr) tr[1] = clock64();
                 tc_fence_after();
                 uint32_t acc[NG];
+                if (p.flags & 8u) {  // timing experiment: no TMEM reads
 #pragma unroll
-                for (int c = 0; c < NG / 16; ++c) {
-                    uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
-                    tmem_ld16(tmem_lane + s * NG + c * 16, dst);
+                    for (int c = 0; c < NG; ++c) acc[c] = c + t;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NG / 16; ++c) {
+                        uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
+                        tmem_ld16(tmem_lane + s * NG + c * 16, dst);
+                    }
                 }
                 tmem_wait_ld();
                 tc_fence_before();
-                mbar_arrive(base + kBarAccEmpty + 8 * s);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(base + kBarAccEmpty + 8 * s);
+                if (tr) tr[2] = clock64();
+                if (p.flags & 64u) continue;  // timing experiment: drain only
 
                 if constexpr (!TAIL) {
-                    const bool keep = colok && (p.rowflag[r] != 0);
-                    const uint32_t stg = base + kOffStage + (rowc & 1) * kRowBytes;
-                    if (leader) bulk_wait_read<1>();  // the store issued two rows ago has drained this buffer
-                    named_bar_sync(1, 128);
-                    if (m >= 1 && m <= kStripPx) {
-                        const int row = m - 1;
-                        const uint32_t rbase = stg + row * 128;
+                    if (inside && !(p.flags & 16u)) {  // flag 16: timing experiment without the stores
+                        const bool keep = colok && (p.rowflag[pr] != 0);
+                        uint8_t* const orow = reinterpret_cast<uint8_t*>(p.out) +
+                                              (static_cast<long long>(pr) * p.canvas_w + cx) * 128;
+                        const float4* const sb = reinterpret_cast<const float4*>(base_ptr + kOffBias);
+                        const float4* const ss = reinterpret_cast<const float4*>(base_ptr + kOffSlope);
 #pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) {
-                            uint32_t pk[4];
+                        for (int c16 = 0; c16 < 4; ++c16) {
+                            uint32_t pk[8];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const int ch = c8 * 8 + j * 2;
-                                float v0 = __uint_as_float(acc[ch]) + p.bias[ch];
-                                float v1 = __uint_as_float(acc[ch + 1]) + p.bias[ch + 1];
-                                v0 = fmaxf(v0, 0.f) + p.slope[ch] * fminf(v0, 0.f);
-                                v1 = fmaxf(v1, 0.f) + p.slope[ch + 1] * fminf(v1, 0.f);
-                                pk[j] = keep ? pack_half2(v0, v1) : 0u;
+                                const int ch = c16 * 16 + j * 4;
+                                const float4 b4 = sb[ch >> 2], a4 = ss[ch >> 2];
+                                float v0 = __uint_as_float(acc[ch]) + b4.x;
+                                float v1 = __uint_as_float(acc[ch + 1]) + b4.y;
+                                float v2 = __uint_as_float(acc[ch + 2]) + b4.z;
+                                float v3 = __uint_as_float(acc[ch + 3]) + b4.w;
+                                v0 = fmaxf(v0, 0.f) + a4.x * fminf(v0, 0.f);
+                                v1 = fmaxf(v1, 0.f) + a4.y * fminf(v1, 0.f);
+                                v2 = fmaxf(v2, 0.f) + a4.z * fminf(v2, 0.f);
+                                v3 = fmaxf(v3, 0.f) + a4.w * fminf(v3, 0.f);
+                                pk[2 * j] = keep ? pack_half2(v0, v1) : 0u;
+                                pk[2 * j + 1] = keep ? pack_half2(v2, v3) : 0u;
                             }
-                            st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            if (p.flags & 4u) st_global_v8_hint(orow + c16 * 32, pk, kPolicyEvictLast);
+                            else st_global_v8(orow + c16 * 32, pk);
                         }
                     }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
-                    if (leader) {
-                        tma_store_3d(&out_map, stg, 0, x0, r);
-                        bulk_commit();
-                    }
-                    ++rowc;
                 } else {
                     constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
-                    const int oy = p.out_y[r];
+                    const int oy = p.out_y[pr];
                     if (ox >= 0 && oy >= 0) {
-                        const uint8_t* sp = p.src + static_cast<long long>(p.src_y[r]) * p.src_stride + sx * 3;
+                        const uint8_t* sp = p.src + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
                         const float xin[3] = {static_cast<float>(sp[0]), static_cast<float>(sp[1]),
                                               static_cast<float>(sp[2])};
 #pragma unroll
@@ -298,7 +404,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
 #pragma unroll
                                 for (int c = 0; c < 3; ++c) {
                                     const int idx = c * S * S + i * S + j;
-                                    const float v = __uint_as_float(acc[idx]) + p.bias[idx];
+                                    const float v = __uint_as_float(acc[idx]) +
+                                                    reinterpret_cast<const float*>(base_ptr + kOffBias)[idx];
                                     // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5))
                                     float o = floorf(fmaf(v, 255.f, xin[c] + 0.5f));
                                     o = fminf(fmaxf(o, 0.f), 255.f);
@@ -310,40 +417,38 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map,
                 }
             }
         }
-        if (!TAIL && leader) bulk_wait<0>();
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
-template <int NG, bool TAIL>
+template <int NG>
 constexpr size_t smem_bytes_t() {
-    return 1024 /*alignment slack*/ + kCtrlBytes + w_bytes(NG) + kGuard + kStages * kRowBytes + kGuard +
-           (TAIL ? 0 : 2 * kRowBytes);
+    return 1024 /*alignment slack*/ + kCtrlBytes + w_bytes(NG) + kGuard + kStages * kRowBytes + kGuard;
 }
 
 }  // namespace
 
-size_t conv_smem_bytes(int ng, bool tail) {
-    return 1024 + kCtrlBytes + w_bytes(ng) + kGuard + kStages * kRowBytes + kGuard + (tail ? 0 : 2 * kRowBytes);
-}
 size_t conv_weight_blob_bytes(int ng) { return w_bytes(ng); }
 
-void pack_conv_weights(const float* w_oihw, int co, int ng, uint16_t* blob) {
+void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16_t* blob) {
     // blob[dx][n = g*ng + o][ci] fp16 with the 128-byte swizzle applied per 128-byte row:
-    // 16-byte chunk c of row n is stored at chunk (c ^ (n & 7)).
+    // 16-byte chunk c of row n is stored at chunk (c ^ (n & 7)).  Group g holds vertical tap
+    // ky = g (forward sweep) or ky = 2 - g (reverse sweep).
     std::memset(blob, 0, w_bytes(ng));
     for (int dx = 0; dx < 3; ++dx)
         for (int g = 0; g < 3; ++g)
             for (int o = 0; o < co; ++o) {
                 const int n = g * ng + o;
+                const int ky = reverse ? 2 - g : g;
                 for (int ci = 0; ci < 64; ++ci) {
-                    const float v = w_oihw[((static_cast<size_t>(o) * 64 + ci) * 3 + g) * 3 + dx];
+                    const float v = w_oihw[((static_cast<size_t>(o) * 64 + ci) * 3 + ky) * 3 + dx];
                     const size_t byte = static_cast<size_t>(dx) * (3 * ng * 128) + static_cast<size_t>(n) * 128 +
                                         (((ci >> 3) ^ (n & 7)) << 4) + (ci & 7) * 2;
                     blob[byte / 2] = f32_to_f16(v);
@@ -354,30 +459,29 @@ void pack_conv_weights(const float* w_oihw, int co, int ng, uint16_t* blob) {
 cudaError_t conv_kernels_init() {
     cudaError_t e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<64, false>()));
+                             static_cast<int>(smem_bytes_t<64>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<16, true>()));
+                             static_cast<int>(smem_bytes_t<16>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<32, true>()));
+                             static_cast<int>(smem_bytes_t<32>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<48, true>()));
+                             static_cast<int>(smem_bytes_t<48>()));
     return e;
 }
 
-cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
-                             const ConvParams& p) {
-    conv3x3_umma_kernel<64, false><<<grid, kConvThreads, smem_bytes_t<64, false>(), st>>>(in_map, out_map, p);
+cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const ConvParams& p) {
+    conv3x3_umma_kernel<64, false><<<grid, kConvThreads, smem_bytes_t<64>(), st>>>(in_map, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p) {
     switch (scale) {
-        case 2: conv3x3_umma_kernel<16, true><<<grid, kConvThreads, smem_bytes_t<16, true>(), st>>>(in_map, in_map, p); break;
-        case 3: conv3x3_umma_kernel<32, true><<<grid, kConvThreads, smem_bytes_t<32, true>(), st>>>(in_map, in_map, p); break;
-        case 4: conv3x3_umma_kernel<48, true><<<grid, kConvThreads, smem_bytes_t<48, true>(), st>>>(in_map, in_map, p); break;
+        case 2: conv3x3_umma_kernel<16, true><<<grid, kConvThreads, smem_bytes_t<16>(), st>>>(in_map, p); break;
+        case 3: conv3x3_umma_kernel<32, true><<<grid, kConvThreads, smem_bytes_t<32>(), st>>>(in_map, p); break;
+        case 4: conv3x3_umma_kernel<48, true><<<grid, kConvThreads, smem_bytes_t<48>(), st>>>(in_map, p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

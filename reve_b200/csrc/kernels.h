@@ -10,8 +10,8 @@ namespace reve {
 
 constexpr int kBoxPx = 128;    // pixels per TMA row box = UMMA M
 constexpr int kStripPx = 126;  // valid output pixels per strip row (box minus the 2 halo columns)
-constexpr int kStages = 6;     // A-row ring depth
-constexpr int kConvThreads = 192;
+constexpr int kStages = 8;     // A-row ring depth
+constexpr int kConvThreads = 320;  // producer warp + MMA warp + 2 x 4 epilogue warps
 
 // Parameters of the tcgen05 3x3 convolution kernels (body: 64->64 + PReLU -> fp16 canvas;
 // tail: 64->3*s*s + PixelShuffle + nearest residual + u8 pack).  Passed as a __grid_constant__
@@ -23,7 +23,11 @@ struct ConvParams {
     const uint8_t* colflag;     // [canvas_w] 1 = pixel of a tile, 0 = gap column
     const uint8_t* rowflag;     // [canvas_h]
     const void* weights;        // pre-swizzled B operand blob of this layer (global memory)
+    __half* out;                // body: output canvas [canvas_h][canvas_w][64] fp16
+    int reverse;                // sweep the strip-rows bottom-up (weights blob packed accordingly)
+    uint32_t flags;             // debug: bit1 = no evict-first on loads, bit2 = evict-last on stores
     DebugBlock* dbg;            // mapped pinned host memory, may be null
+    long long* trace;           // debug timeline of CTA 0 (device memory, may be null)
     // tail only
     const uint8_t* src;         // u8 RGB input frame (device)
     uint8_t* dst;               // u8 RGB output frame (device)
@@ -50,14 +54,13 @@ struct Conv0Params {
     float slope[64];
 };
 
-size_t conv_smem_bytes(int ng, bool tail);
 size_t conv_weight_blob_bytes(int ng);
 // Packs OIHW fp32 weights [co][64][3][3] into the pre-swizzled fp16 B-operand blob for group
-// width `ng` (co <= ng; missing output channels are zero).
-void pack_conv_weights(const float* w_oihw, int co, int ng, uint16_t* blob);
+// width `ng` (co <= ng; missing output channels are zero); `reverse` = blob for a bottom-up sweep.
+void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16_t* blob);
 
 cudaError_t conv_kernels_init();  // opt-in shared memory attributes; call once per device
-cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
+cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const ConvParams& p);
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p);
 cudaError_t launch_conv0(cudaStream_t st, const Conv0Params& p);
 
