@@ -1,0 +1,265 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle.
+
+Acceptance bar (BASELINE.json north_star): >= 99.9 % of u8 pixels within +-1 LSB and PSNR >= 50 dB
+against the fp32 oracle evaluated with identical tile / pre-pad semantics.  Activations are stored
+as fp16 on the device, so intermediate features are compared with a tolerance of 2e-2 + 2e-2*|ref|.
+"""
+import ctypes as C
+import glob
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import reve_b200
+from helpers import feature_report, oracle_canvas
+from oracle import srvgg
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+WITHIN1, PSNR = 0.999, 50.0
+
+
+def check(out, ref):
+    par = srvgg.parity(out, ref)
+    assert par["within1"] >= WITHIN1 and par["psnr"] >= PSNR, par
+    return par
+
+
+def test_native_library_is_loaded_and_sees_the_gpu(lib):
+    n = C.c_int()
+    assert lib.reve_device_count(C.byref(n)) == 0 and n.value >= 1
+    loaded = open("/proc/self/maps").read()
+    assert "libreve_cuda.so" in loaded
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors(path):
+    g = np.load(path)
+    scale, seed, tile, prepad = int(g["scale"]), int(g["seed"]), int(g["tile"]), int(g["prepad"])
+    frame = g["frame"]
+    model = reve_b200.Model.random(scale, seed)
+    with reve_b200.Upscaler(model, frame.shape[1], frame.shape[0], tile=tile, prepad=prepad) as up:
+        out = up.upscale(frame)
+    assert out.shape == g["out"].shape
+    check(out, g["out"])
+
+
+@pytest.mark.parametrize("w,h,scale,tile,grid", [
+    (100, 30, 2, 0, "1"),      # one CTA walks the whole strip: full 3-slot window, ring wrap
+    (300, 40, 2, 0, "2"),      # CTAs spanning two strips
+    (300, 200, 2, 0, None),    # 148 CTAs, 4-5 rows each
+    (200, 150, 2, 64, None),   # several tiles: gap rows/columns, reflect at every border
+    (137, 91, 3, 50, None),    # ragged sizes, x3 (N padded to 32)
+    (150, 90, 4, 0, "3"),      # x4 (N = 48)
+])
+def test_per_layer_features_and_output(w, h, scale, tile, grid, monkeypatch):
+    if grid:
+        monkeypatch.setenv("REVE_DEBUG_GRID", grid)
+    wts = srvgg.make_weights(scale, 1234)
+    frame = srvgg.synthetic_frame(w, h, 5, "random")
+    model = reve_b200.Model.random(scale, 1234)
+    with reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=2) as up:
+        for layer in (1, 2, 3, 10, 17):
+            dev = up.debug_features(frame, layer)
+            ref = oracle_canvas(frame, wts, tile, 10, layer)
+            assert dev.shape == ref.shape
+            rep = feature_report(dev, ref)
+            assert rep["bad_frac"] == 0.0, (layer, rep)
+        out = up.upscale(frame)
+    check(out, srvgg.upscale(frame, wts, tile=tile, prepad=10))
+
+
+def test_one_hot_weights_pin_tap_and_channel_layout():
+    """A single non-zero weight per layer: any mix-up of (ky, kx, ci, co) or of the PixelShuffle
+    order moves the response somewhere else."""
+    scale = 2
+    wts = srvgg.make_weights(scale, 1)
+    for k in range(18):
+        wts.conv_w[k][...] = 0
+        wts.conv_b[k][...] = 0
+    rng = np.random.default_rng(3)
+    wts.conv_w[0][5, 1, 0, 2] = 1.0
+    prev = 5
+    for k in range(1, 17):
+        co, ky, kx = int(rng.integers(0, 64)), int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        wts.conv_w[k][co, prev, ky, kx] = 1.0
+        prev = co
+    wts.conv_w[17][7, prev, 2, 0] = 0.5
+    import tempfile
+    d = tempfile.mkdtemp()
+    srvgg.write_ncnn(wts, d + "/m.param", d + "/m.bin", fp16=True)
+    model = reve_b200.Model.load_ncnn(d + "/m.param", d + "/m.bin")
+    frame = srvgg.synthetic_frame(90, 70, 8, "random")
+    with reve_b200.Upscaler(model, 90, 70, tile=0, prepad=10) as up:
+        out = up.upscale(frame)
+        feat = up.debug_features(frame, 17)
+    ref = srvgg.upscale(frame, wts, tile=0, prepad=10)
+    par = srvgg.parity(out, ref)
+    assert par["within1"] == 1.0 and par["exact"] > 0.95, par   # x/255 passes through fp16 storage
+    ref_feat = oracle_canvas(frame, wts, 0, 10, 17)
+    assert feature_report(feat, ref_feat)["bad_frac"] == 0.0
+    assert np.abs(ref_feat).max() > 0.1      # the probe actually lights something up
+
+
+def test_edge_frames_and_strides():
+    wts = srvgg.make_weights(2, 21)
+    model = reve_b200.Model.random(2, 21)
+    for (w, h, tile, prepad) in ((11, 11, 200, 10), (1, 1, 0, 0), (127, 1, 0, 0), (1, 130, 64, 0), (253, 12, 126, 10)):
+        frame = srvgg.synthetic_frame(w, h, w + h, "random")
+        with reve_b200.Upscaler(model, w, h, tile=tile, prepad=prepad) as up:
+            out = up.upscale(frame)
+            # strided (non-packed rows) input and output buffers
+            big_in = np.zeros((h, w + 5, 3), np.uint8)
+            big_in[:, :w] = frame
+            big_out = np.full((h * 2, w * 2 + 7, 3), 77, np.uint8)
+            up.submit(big_in[:, :w], big_out[:, :w * 2], 5)
+            assert up.wait() == 5
+        ref = srvgg.upscale(frame, wts, tile=tile, prepad=prepad)
+        check(out, ref)
+        assert np.array_equal(big_out[:, :w * 2], out)
+        assert (big_out[:, w * 2:] == 77).all()          # bytes beyond the row are untouched
+
+
+def test_ring_fifo_order_busy_and_empty():
+    model = reve_b200.Model.random(2, 3)
+    w, h = 96, 64
+    wts = srvgg.make_weights(2, 3)
+    frames = [srvgg.synthetic_frame(w, h, i, "edges" if i % 2 else "random") for i in range(7)]
+    with reve_b200.Upscaler(model, w, h, tile=200, prepad=10, ring_depth=3) as up:
+        with pytest.raises(reve_b200.ReveError) as e:
+            up.wait()
+        assert e.value.status == -8                       # REVE_E_EMPTY
+        ins = [up.pinned((h, w, 3)) for _ in range(3)]
+        outs = [up.pinned((h * 2, w * 2, 3)) for _ in range(3)]
+        for i in range(3):
+            ins[i][...] = frames[i]
+            up.submit(ins[i], outs[i], 100 + i)
+        with pytest.raises(reve_b200.ReveError) as e:
+            up.submit(ins[0], outs[0], 999)
+        assert e.value.status == -7                       # REVE_E_BUSY
+        got = []
+        for i in range(3):
+            tag = up.wait()
+            got.append((tag, outs[i].copy()))
+        assert [t for t, _ in got] == [100, 101, 102]
+        for i, (_, o) in enumerate(got):
+            check(o, srvgg.upscale(frames[i], wts, tile=200, prepad=10))
+        # pipelined helper over more frames than ring slots
+        res = [np.empty((h * 2, w * 2, 3), np.uint8) for _ in frames]
+        order = []
+        assert up.upscale_many(frames, res, on_done=order.append) == len(frames)
+        assert order == list(range(len(frames)))
+        for f, o in zip(frames, res):
+            check(o, srvgg.upscale(f, wts, tile=200, prepad=10))
+
+
+def test_device_resident_path_matches_submit_path():
+    import torch
+    model = reve_b200.Model.random(2, 4)
+    w, h, n = 160, 90, 3
+    frames = np.stack([srvgg.synthetic_frame(w, h, 40 + i, "random") for i in range(n)])
+    with reve_b200.Upscaler(model, w, h, tile=64, prepad=10) as up:
+        d_in = torch.from_numpy(frames).cuda()
+        d_out = torch.zeros((n, h * 2, w * 2, 3), dtype=torch.uint8, device="cuda")
+        up.upscale_device(d_in.data_ptr(), d_out.data_ptr(), n)
+        up.sync()
+        dev = d_out.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(dev[i], up.upscale(frames[i]))
+        prof = up.profile()
+        assert prof["launches_body"] == 16 * 2 * n and prof["launches_conv0"] == 2 * n and prof["launches_tail"] == 2 * n
+
+
+def test_results_are_deterministic_and_contexts_are_independent():
+    model = reve_b200.Model.random(3, 6)
+    w, h = 120, 80
+    frame = srvgg.synthetic_frame(w, h, 9, "edges")
+    results = {}
+
+    def run(key):
+        with reve_b200.Upscaler(model, w, h, tile=50, prepad=10) as up:
+            a = up.upscale(frame)
+            b = up.upscale(frame)
+            results[key] = (a, b)
+
+    ts = [threading.Thread(target=run, args=(k,)) for k in range(2)]   # one context per host thread
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    a0, b0 = results[0]
+    a1, b1 = results[1]
+    assert np.array_equal(a0, b0) and np.array_equal(a0, a1) and np.array_equal(a1, b1)
+    check(a0, srvgg.upscale(frame, srvgg.make_weights(3, 6), tile=50, prepad=10))
+
+
+def test_full_size_1080p_properties_and_oracle():
+    """BASELINE.json configs[1] at full size: size-independent properties plus one oracle frame."""
+    w, h, scale = 1920, 1080, 2
+    wts = srvgg.make_weights(scale, 1234)
+    model = reve_b200.Model.random(scale, 1234)
+    frame = srvgg.synthetic_frame(w, h, 77, "edges")
+    frame[::3, ::5] = srvgg.synthetic_frame(w, h, 78, "random")[::3, ::5]     # add texture
+    with reve_b200.Upscaler(model, w, h, tile=200, prepad=10) as up:
+        out = up.upscale(frame)
+        assert np.array_equal(out, up.upscale(frame))                          # idempotent / deterministic
+    assert out.shape == (h * scale, w * scale, 3)
+    # tile locality: tile (0,0) only sees frame[0:210, 0:210]; a 210x210 frame has the same first tile
+    crop = np.ascontiguousarray(frame[:210, :210])
+    with reve_b200.Upscaler(model, 210, 210, tile=200, prepad=10) as up:
+        small = up.upscale(crop)
+    assert np.array_equal(out[:400, :400], small[:400, :400])
+    # an interior tile equals the same window run as a stand-alone frame whose borders are real pixels
+    # (tile (2,3): x in [600,800), y in [400,600)); compare through the oracle on that window only
+    win = np.ascontiguousarray(frame[390:610, 590:810])                        # tile + 10 px of real neighbours
+    x = (win.astype(np.float32) * np.float32(1 / 255.0)).transpose(2, 0, 1)
+    ref_win = srvgg.quantise(srvgg.forward(x, wts)[:, 20:-20, 20:-20].transpose(1, 2, 0))
+    check(out[800:1200, 1200:1600], ref_win)
+    # whole frame against the oracle (about 4 s of CPU)
+    check(out, srvgg.upscale(frame, wts, tile=200, prepad=10))
+
+
+def test_whole_frame_mode_720p_x4_against_oracle_window():
+    """BASELINE.json configs[2] geometry (1280x720 x4), whole-frame mode, checked on windows."""
+    w, h, scale = 1280, 720, 4
+    wts = srvgg.make_weights(scale, 5)
+    model = reve_b200.Model.random(scale, 5)
+    frame = srvgg.synthetic_frame(w, h, 31, "random")
+    with reve_b200.Upscaler(model, w, h, tile=0, prepad=10) as up:
+        out = up.upscale(frame)
+    assert out.shape == (h * 4, w * 4, 3)
+    # receptive-field radius is 18 px: a window with a 20 px margin reproduces the interior exactly
+    for (x0, y0) in ((300, 200), (1100, 560)):
+        win = np.ascontiguousarray(frame[y0 - 20:y0 + 84, x0 - 20:x0 + 84])
+        x = (win.astype(np.float32) * np.float32(1 / 255.0)).transpose(2, 0, 1)
+        ref = srvgg.quantise(srvgg.forward(x, wts)[:, 80:-80, 80:-80].transpose(1, 2, 0))
+        check(out[y0 * 4:(y0 + 64) * 4, x0 * 4:(x0 + 64) * 4], ref)
+    # top-left corner: reflect-101 pre-pad of 10 px
+    corner = srvgg.upscale(np.ascontiguousarray(frame[:120, :120]), wts, tile=0, prepad=10)
+    check(out[:80 * 4, :80 * 4], corner[:80 * 4, :80 * 4])
+
+
+def test_upscale_segment_directory_contract(tmp_path):
+    """Mirror of Video::upscale_segment: frames in, same names out, one 'done' line per frame."""
+    import io
+    indir, outdir = tmp_path / "tmp_frames" / "0", tmp_path / "out_frames" / "0"
+    indir.mkdir(parents=True)
+    frames = [srvgg.synthetic_frame(80, 60, i, "edges") for i in range(5)]
+    import cv2
+    for i, f in enumerate(frames):
+        assert cv2.imwrite(str(indir / f"frame{i + 1:08d}.png"), f[:, :, ::-1])
+    log = io.StringIO()
+    model = reve_b200.Model.random(2, 8)
+    n = reve_b200.upscale_segment(str(indir), str(outdir), 2, model=model, progress=log)
+    assert n == 5
+    lines = [l for l in log.getvalue().splitlines() if "done" in l]     # what reve-cli/src/main.rs:269 counts
+    assert len(lines) == 5
+    wts = srvgg.make_weights(2, 8)
+    for i, f in enumerate(frames):
+        got = cv2.imread(str(outdir / f"frame{i + 1:08d}.png"), cv2.IMREAD_COLOR)[:, :, ::-1]
+        check(got, srvgg.upscale(f, wts, tile=200, prepad=10))
+    with pytest.raises(ValueError):
+        reve_b200.upscale_segment(str(indir), str(tmp_path / "o2"), 3, model=model)   # scale / model mismatch
