@@ -52,7 +52,10 @@ struct reve_ctx {
     uint8_t *d_colflag = nullptr, *d_rowflag = nullptr;
     int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr;
     void* d_wblob[kNumConv] = {};  // per layer: forward-sweep blob followed by the reverse-sweep blob
-    CUtensorMap map_in[2];
+    CUtensorMap map_in[2], map_out[2];
+    CUtensorMap map_flat0;   // act[0] as a flat [pixels][64] tensor (conv0 output tiles of 128 pixels)
+    void* d_w0 = nullptr;    // conv0 B operand
+    int grid0 = 0;
     Conv0Params c0;
     ConvParams body[kNumBody];
     ConvParams tail;
@@ -131,11 +134,11 @@ int enqueue_frame(reve_ctx* ctx, const uint8_t* d_in, long long in_stride, uint8
     Conv0Params c0 = ctx->c0;
     c0.src = d_in;
     c0.src_stride = in_stride;
-    CK(ctx, launch_conv0(ctx->s_comp, c0));
+    CK(ctx, launch_conv0(ctx->s_comp, ctx->grid0, ctx->map_flat0, c0));
     ctx->prof.launches_conv0++;
     prof_mark(ctx, 0);
     for (int k = 0; k < kNumBody && k + 1 < stop_after_layers; ++k) {
-        CK(ctx, launch_conv_body(ctx->s_comp, ctx->grid, ctx->map_in[k & 1], ctx->body[k]));
+        CK(ctx, launch_conv_body(ctx->s_comp, ctx->grid, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], ctx->body[k]));
         ctx->prof.launches_body++;
         prof_mark(ctx, 1);
     }
@@ -191,6 +194,7 @@ void destroy_ctx(reve_ctx* ctx) {
     cudaFree(ctx->d_outx);
     cudaFree(ctx->d_outy);
     for (void* p : ctx->d_wblob) cudaFree(p);
+    cudaFree(ctx->d_w0);
     cudaFree(ctx->d_trace);
     if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -218,6 +222,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     const int cw = g.canvas_w(), ch = g.canvas_h();
 
     CK(ctx, conv_kernels_init());
+    CK(ctx, conv0_kernel_init());
     CK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -253,9 +258,26 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
     for (int i = 0; i < 2; ++i) {
         if ((rc = encode_map(ctx, enc, &ctx->map_in[i], ctx->act[i], cw, ch, kBoxPx))) return rc;
+        if ((rc = encode_map(ctx, enc, &ctx->map_out[i], ctx->act[i], cw, ch, kStripPx))) return rc;
+    }
+
+    {
+        const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(cw) * ch};
+        const cuuint64_t gstride[1] = {128};
+        const cuuint32_t box[2] = {64, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&ctx->map_flat0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ctx->act[0], gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_err(ctx, REVE_E_CUDA, "cuTensorMapEncodeTiled (flat map) failed");
     }
 
     // weights
+    {
+        std::vector<uint16_t> blob(conv0_weight_blob_bytes() / 2);
+        pack_conv0_weights(m.conv[0].w.data(), blob.data());
+        if ((rc = upload(ctx, &ctx->d_w0, blob.data(), blob.size() * 2))) return rc;
+    }
     const int tail_ng = m.scale == 2 ? 16 : (m.scale == 3 ? 32 : 48);
     for (int k = 1; k < kNumConv; ++k) {
         const int ng = (k == kNumConv - 1) ? tail_ng : 64;
@@ -267,20 +289,24 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     }
 
     // parameter blocks
+    uint32_t dflags = 0;
+    if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) dflags = static_cast<uint32_t>(std::atoi(fe));
     Conv0Params& c0 = ctx->c0;
     std::memset(&c0, 0, sizeof c0);
     c0.canvas_w = cw;
     c0.canvas_h = ch;
     c0.src_x = ctx->d_srcx;
     c0.src_y = ctx->d_srcy;
-    c0.dst = ctx->act[0];
+    c0.weights = ctx->d_w0;
+    c0.dbg = ctx->dbg_dev;
+    c0.flags = dflags;
     for (int co = 0; co < 64; ++co) {
-        for (int c = 0; c < 3; ++c)
-            for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx)
-                    c0.w[(ky * 3 + kx) * 3 + c][co] = m.conv[0].w[((static_cast<size_t>(co) * 3 + c) * 3 + ky) * 3 + kx];
         c0.bias[co] = m.conv[0].b[co];
         c0.slope[co] = m.conv[0].slope[co];
+    }
+    {
+        const long long tiles0 = (static_cast<long long>(cw) * ch + 127) / 128;
+        ctx->grid0 = static_cast<int>(tiles0 < ctx->sm_count ? tiles0 : ctx->sm_count);
     }
     const int n_strips = (cw + kStripPx - 1) / kStripPx;
     const long long total = static_cast<long long>(n_strips) * ch;
@@ -292,8 +318,6 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     }
     // Debug flags (tests / experiments): bit0 = never sweep in reverse, bit1 = no evict-first hint on
     // activation loads, bit2 = evict-last hint on activation stores.
-    uint32_t dflags = 0;
-    if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) dflags = static_cast<uint32_t>(std::atoi(fe));
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         std::memset(&p, 0, sizeof p);

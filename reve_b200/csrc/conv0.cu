@@ -1,80 +1,295 @@
-// First convolution (3 -> 64, 3x3) + PReLU, fused with the pre-processing of the upscaler spawned
-// at reference reve-shared/src/lib.rs:134-147 (SURVEY.md section 2.3, K1 + K2): u8 RGB gather
-// with the reflect-101 pre-pad, /255, zero padding at tile borders, canvas layout, fp16 NHWC out.
+// First convolution (3 -> 64, 3x3) + PReLU on tcgen05 tensor cores, fused with the pre-processing
+// of the upscaler spawned at reference reve-shared/src/lib.rs:134-147 (SURVEY.md section 2.3,
+// K1 + K2): u8 RGB gather with the reflect-101 pre-pad, zero padding at tile borders, /255, canvas
+// layout, fp16 NHWC out.
 //
-// 0.29 % of the network's FLOPs: CUDA cores, one canvas pixel per thread, all 1 728 weights read
-// as constant-bank operands of the FFMAs (the parameter block is a __grid_constant__).
+// The layer is a GEMM with K = 27 (padded to 32): M = 128 consecutive canvas pixels (raster order,
+// no halo: the im2col row of a pixel already holds its 3x3x3 neighbourhood), N = 64.  Producer
+// warps build the im2col A tile straight from the u8 frame into shared memory (exact integers
+// 0..255 as fp16, canonical K-major no-swizzle core-matrix layout), one warp issues two K=16 MMAs
+// per tile into a ring of TMEM accumulators, and two epilogue groups apply (acc/255 + bias), PReLU,
+// gap zeroing and write the row-major fp16 tile with one TMA store.
+// Warp roles (544 threads): warps 0-7 = two producer groups (alternate tiles), warp 8 = TMEM
+// allocator + MMA issuer, warps 9-16 = two epilogue groups (alternate tiles).  The src_x / src_y
+// geometry tables are cached in shared memory so the gather needs one global round trip per tile.
 #include "kernels.h"
+
+#include <cstring>
+
+#include "model.h"
 
 namespace reve {
 
 namespace {
 
-constexpr int kConv0Threads = 128;
+constexpr int kProducerWarps = 8;            // two groups of 4: alternate tiles
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kFirstEpiWarp = kMmaWarp + 1;  // 8 epilogue warps; TMEM lane quarter = warp % 4
+constexpr int kThreads = (kFirstEpiWarp + 8) * 32;
+constexpr int kMaxTableInts = 12288;         // src_x / src_y cached in shared memory when they fit (48 KB)
+constexpr int kStagesA = 4;
+constexpr int kTileA = 128 * 64;       // 8 KB: 128 px x 32 k x fp16
+constexpr int kAccBufs = 4;            // TMEM accumulator ring: 4 x 64 columns
+constexpr int kWBytes0 = 64 * 64;      // 4 KB: 64 co x 32 k x fp16
+constexpr int kStageOut = 128 * 128;   // 16 KB output staging per epilogue group
 
-__global__ void __launch_bounds__(kConv0Threads)
-conv0_kernel(const __grid_constant__ Conv0Params p) {
-    const int cx = blockIdx.x * kConv0Threads + threadIdx.x;
-    const int cy = blockIdx.y;
-    if (cx >= p.canvas_w) return;
-    uint4* dst = reinterpret_cast<uint4*>(p.dst + (static_cast<size_t>(cy) * p.canvas_w + cx) * 64);
+// control block
+constexpr int kBarW = 0;
+constexpr int kBarFull = 8;                          // [kStagesA]
+constexpr int kBarEmpty = kBarFull + 8 * kStagesA;   // [kStagesA]
+constexpr int kBarAccFull = kBarEmpty + 8 * kStagesA;  // [kAccBufs]
+constexpr int kBarAccEmpty = kBarAccFull + 8 * kAccBufs;
+constexpr int kTmemPtr = 512;
+constexpr int kCtrl = 1024;
+constexpr int kOffW = kCtrl;
+constexpr int kOffA = kOffW + kWBytes0;
+constexpr int kOffOut = kOffA + kStagesA * kTileA;
+constexpr int kOffTab = kOffOut + 2 * kStageOut;
+constexpr int kSmem = 1024 + kOffTab + kMaxTableInts * 4;
 
-    const int sxc = p.src_x[cx];
-    const int syc = p.src_y[cy];
-    if (sxc < 0 || syc < 0) {  // gap pixel: must read as zero in every later layer
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
-        return;
+enum : uint32_t { TAG0_W = 11, TAG0_EMPTY = 12, TAG0_FULL = 13, TAG0_ACC_EMPTY = 14, TAG0_ACC_FULL = 15 };
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between core matrices that
+// are adjacent in K, SBO = distance between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_u8x2(unsigned a, unsigned b) {
+    const __half2 h = __halves2half2(__ushort2half_rn(static_cast<unsigned short>(a)),
+                                     __ushort2half_rn(static_cast<unsigned short>(b)));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ Conv0Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* const base_ptr = smem_raw + (base - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DebugBlock* const dbg = p.dbg;
+
+    if (threadIdx.x == 0) {
+        mbar_init(base + kBarW, 1);
+        for (int s = 0; s < kStagesA; ++s) {
+            mbar_init(base + kBarFull + 8 * s, 4);   // one arrive per producer warp
+            mbar_init(base + kBarEmpty + 8 * s, 1);
+        }
+        for (int s = 0; s < kAccBufs; ++s) {
+            mbar_init(base + kBarAccFull + 8 * s, 1);
+            mbar_init(base + kBarAccEmpty + 8 * s, 4);
+        }
+        fence_mbar_init();
     }
-    float x[27];
+    if (warp == kMmaWarp) {
+        tmem_alloc(base + kTmemPtr, kAccBufs * 64);
+        tmem_relinquish();
+    }
+    const int CW = p.canvas_w, CHh = p.canvas_h;
+    const bool tab_smem = (CW + CHh) <= kMaxTableInts;
+    int* const tab = reinterpret_cast<int*>(base_ptr + kOffTab);
+    if (tab_smem) {
+        for (int i = threadIdx.x; i < CW; i += kThreads) tab[i] = p.src_x[i];
+        for (int i = threadIdx.x; i < CHh; i += kThreads) tab[CW + i] = p.src_y[i];
+    }
+    const int* const tx = tab_smem ? tab : p.src_x;
+    const int* const ty = tab_smem ? tab + CW : p.src_y;
+    if (warp == kFirstEpiWarp && lane == 0) {
+        prefetch_tmap(&out_map);
+        mbar_arrive_expect_tx(base + kBarW, kWBytes0);
+        bulk_load_1d(base + kOffW, p.weights, kWBytes0, base + kBarW);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kTmemPtr);
+
+    const long long npx = static_cast<long long>(CW) * CHh;
+    const int n_tiles = static_cast<int>((npx + 127) / 128);
+
+    if (warp < kProducerWarps) {
+        // ------------------------------------------------------------------ im2col producers
+        const int pg = warp >> 2;
+        const int m = (warp & 3) * 32 + lane;
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            if ((j & 1) != static_cast<uint32_t>(pg)) continue;
+            const uint32_t stage = j % kStagesA, use = j / kStagesA;
+            const long long px = static_cast<long long>(tile) * 128 + m;
+            uint32_t w[16];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int yy = cy + ky - 1;
-        const int sy = (yy >= 0 && yy < p.canvas_h) ? p.src_y[yy] : -1;
+            for (int i = 0; i < 16; ++i) w[i] = 0u;
+            if (px < npx) {
+                const int cy = static_cast<int>(px / CW), cx = static_cast<int>(px - static_cast<long long>(cy) * CW);
+                if (tx[cx] >= 0 && ty[cy] >= 0) {
+                    unsigned v[28];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = cx + kx - 1;
-            const int sx = (xx >= 0 && xx < p.canvas_w) ? p.src_x[xx] : -1;
-            if (sy >= 0 && sx >= 0) {
-                const uint8_t* s = p.src + static_cast<long long>(sy) * p.src_stride + sx * 3;
-                x[(ky * 3 + kx) * 3 + 0] = static_cast<float>(s[0]) * (1.0f / 255.0f);
-                x[(ky * 3 + kx) * 3 + 1] = static_cast<float>(s[1]) * (1.0f / 255.0f);
-                x[(ky * 3 + kx) * 3 + 2] = static_cast<float>(s[2]) * (1.0f / 255.0f);
-            } else {
-                x[(ky * 3 + kx) * 3 + 0] = 0.f;
-                x[(ky * 3 + kx) * 3 + 1] = 0.f;
-                x[(ky * 3 + kx) * 3 + 2] = 0.f;
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int yy = cy + ky - 1;
+                        const int sy = (yy >= 0 && yy < CHh) ? ty[yy] : -1;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int xx = cx + kx - 1;
+                            const int sx = (xx >= 0 && xx < CW) ? tx[xx] : -1;
+                            const int t = (ky * 3 + kx) * 3;
+                            if (sy >= 0 && sx >= 0) {
+                                const uint8_t* s = p.src + static_cast<long long>(sy) * p.src_stride + sx * 3;
+                                v[t] = s[0];
+                                v[t + 1] = s[1];
+                                v[t + 2] = s[2];
+                            } else {
+                                v[t] = v[t + 1] = v[t + 2] = 0u;
+                            }
+                        }
+                    }
+                    v[27] = 0u;
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) w[i] = pack_u8x2(v[2 * i], v[2 * i + 1]);
+                }
+            }
+            mbar_wait(base + kBarEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG0_EMPTY, j);
+            // element (row m, 16-byte k-chunk c) at (m/8)*512 + c*128 + (m%8)*16
+            const uint32_t dst = base + kOffA + stage * kTileA + (m >> 3) * 512 + (m & 7) * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st_shared_v4(dst + c * 128, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(base + kBarFull + 8 * stage);
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        mbar_wait(base + kBarW, 0, dbg, TAG0_W);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(128, 64);
+        constexpr uint32_t lbo = 128u, sbo = 512u;  // verified on B200: LBO = K-adjacent core matrices, SBO = 8-row groups
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const uint32_t stage = j % kStagesA, use = j / kStagesA;
+            const uint32_t buf = j % kAccBufs, ubuf = j / kAccBufs;
+            mbar_wait(base + kBarAccEmpty + 8 * buf, (ubuf & 1) ^ 1, dbg, TAG0_ACC_EMPTY, j);
+            mbar_wait(base + kBarFull + 8 * stage, use & 1, dbg, TAG0_FULL, j);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a = base + kOffA + stage * kTileA;
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+                    umma_f16(tmem_base + buf * 64, umma_desc_nosw(a + s * 256, lbo, sbo),
+                             umma_desc_nosw(base + kOffW + s * 256, lbo, sbo), idesc, s ? 1u : 0u);
+                umma_commit(base + kBarEmpty + 8 * stage);
+                umma_commit(base + kBarAccFull + 8 * buf);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int grp = (warp - kFirstEpiWarp) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t stg = base + kOffOut + grp * kStageOut;
+        const bool gleader = (q == 0 && lane == 0);
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            if ((j & 1) != static_cast<uint32_t>(grp)) continue;
+            const uint32_t buf = j % kAccBufs, ubuf = j / kAccBufs;
+            const long long px = static_cast<long long>(tile) * 128 + m;
+            bool keep = false;
+            if (px < npx) {
+                const int cy = static_cast<int>(px / CW), cx = static_cast<int>(px - static_cast<long long>(cy) * CW);
+                keep = (tx[cx] >= 0) && (ty[cy] >= 0);
+            }
+            mbar_wait(base + kBarAccFull + 8 * buf, ubuf & 1, dbg, TAG0_ACC_FULL, j);
+            tc_fence_after();
+            if (gleader) bulk_wait_read<0>();   // this group's previous tile has left the staging buffer
+            named_bar_sync(1 + grp, 128);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t acc[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
+                    tmem_ld16(tmem_lane + buf * 64 + half * 32 + c * 16, dst);
+                }
+                tmem_wait_ld();
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(base + kBarAccEmpty + 8 * buf);
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int ch = half * 32 + c8 * 8 + jj * 2;
+                        float v0 = fmaf(__uint_as_float(acc[c8 * 8 + jj * 2]), 1.0f / 255.0f, p.bias[ch]);
+                        float v1 = fmaf(__uint_as_float(acc[c8 * 8 + jj * 2 + 1]), 1.0f / 255.0f, p.bias[ch + 1]);
+                        v0 = fmaxf(v0, 0.f) + p.slope[ch] * fminf(v0, 0.f);
+                        v1 = fmaxf(v1, 0.f) + p.slope[ch + 1] * fminf(v1, 0.f);
+                        pk[jj] = keep ? pack_half2(v0, v1) : 0u;
+                    }
+                    st_shared_v4(stg + m * 128 + (((half * 4 + c8) ^ (m & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + grp, 128);
+            if (gleader) {
+                tma_store_2d(&out_map, stg, 0, tile * 128);
+                bulk_commit();
             }
         }
+        if (gleader) bulk_wait<0>();
     }
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = p.bias[c8 * 8 + j];
-#pragma unroll
-        for (int t = 0; t < 27; ++t) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[t], p.w[t][c8 * 8 + j], acc[j]);
-        }
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float v0 = acc[2 * j], v1 = acc[2 * j + 1];
-            v0 = fmaxf(v0, 0.f) + p.slope[c8 * 8 + 2 * j] * fminf(v0, 0.f);
-            v1 = fmaxf(v1, 0.f) + p.slope[c8 * 8 + 2 * j + 1] * fminf(v1, 0.f);
-            const __half2 h = __floats2half2_rn(v0, v1);
-            pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        dst[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kAccBufs * 64);
     }
 }
 
 }  // namespace
 
-cudaError_t launch_conv0(cudaStream_t st, const Conv0Params& p) {
-    const dim3 grid((p.canvas_w + kConv0Threads - 1) / kConv0Threads, p.canvas_h);
-    conv0_kernel<<<grid, kConv0Threads, 0, st>>>(p);
+size_t conv0_weight_blob_bytes() { return kWBytes0; }
+
+void pack_conv0_weights(const float* w_oihw, uint16_t* blob) {
+    // B operand [co = 64][k = 32] fp16, k = (ky*3 + kx)*3 + c (27 used), K-major no-swizzle core-matrix
+    // layout: element (co, k) at (co/8)*512 + (k/8)*128 + (co%8)*16 + (k%8)*2 bytes.
+    std::memset(blob, 0, kWBytes0);
+    for (int co = 0; co < 64; ++co)
+        for (int c = 0; c < 3; ++c)
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int k = (ky * 3 + kx) * 3 + c;
+                    const float v = w_oihw[((static_cast<size_t>(co) * 3 + c) * 3 + ky) * 3 + kx];
+                    const size_t byte = static_cast<size_t>(co / 8) * 512 + (k / 8) * 128 + (co % 8) * 16 + (k % 8) * 2;
+                    blob[byte / 2] = f32_to_f16(v);
+                }
+}
+
+cudaError_t conv0_kernel_init() {
+    return cudaFuncSetAttribute(conv0_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+}
+
+cudaError_t launch_conv0(cudaStream_t st, int grid, const CUtensorMap& out_map, const Conv0Params& p) {
+    conv0_umma_kernel<<<grid, kThreads, kSmem, st>>>(out_map, p);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,7 @@
 //     last in layer l are the rows it reads first in layer l+1, while they are still in L2.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warp-
 // uniform code, one elected lane issues), warps 2..9 = two epilogue groups that take alternate
-// output rows (TMEM -> registers -> bias/PReLU -> fp16 -> 256-bit global stores, or for the tail:
+// output rows (TMEM -> registers -> bias/PReLU -> fp16 -> swizzled smem -> TMA store, or for the tail:
 // bias -> PixelShuffle + residual -> u8 -> global).
 #include "kernels.h"
 
@@ -84,13 +84,22 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t lo) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <int NG, bool TAIL>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ ConvParams p) {
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                    const __grid_constant__ ConvParams p) {
     constexpr int kWBytes = w_bytes(NG);
     constexpr int kTmemCols = tmem_cols(NG);
     constexpr int kOffW = kCtrlBytes;
     constexpr int kOffRing = kOffW + kWBytes + kGuard;
+    constexpr int kOffStage = kOffRing + kStages * kRowBytes + kGuard;  // body: 2 x 16 KB output staging (one per group)
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -117,7 +126,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         tmem_alloc(base + kTmemPtr, kTmemCols);
         tmem_relinquish();
     }
-    if (warp == 0 && lane == 0) prefetch_tmap(&in_map);
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&in_map);
+        if (!TAIL) prefetch_tmap(&out_map);
+    }
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
         // bias / PReLU slopes: shared-memory copies, read back as broadcast LDS.128 in the epilogue
         // (constant-bank operands turn into long-latency LDCU loads on sm_100)
@@ -145,7 +157,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
                 const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
                 for (int y = y_lo; y <= y_hi; ++y, ++i) {
-                    const uint32_t stage = i & (kStages - 1), use = i / kStages;
+                    const uint32_t stage = i % kStages, use = i / kStages;
                     mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
                     if (p.flags & 32u) {  // timing experiment: no TMA traffic
                         mbar_arrive(base + kBarAFull + 8 * stage);
@@ -174,142 +186,154 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const uint32_t ring_lo = lo_flags | ((base + kOffRing) >> 4);
         constexpr uint32_t kG = NG * 8;        // one group of B rows, in 16-byte units
         constexpr uint32_t kDx = 3 * NG * 8;   // one dx block of B
-        static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
+                // Issue helpers (called by the elected lane only).  Part 1 = first K-step (the fresh group
+        // overwrites, the others accumulate) plus three more K-steps; part 2 = the other eight.
+        auto issue_part1 = [&](uint32_t a_lo, int s0) {
+            const uint64_t a0 = mk_desc(desc_hi, a_lo - 8);
+            const uint32_t d = tmem_base + s0 * NG;
+            if (s0 <= 5) {
+                umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
+#pragma unroll
+                for (int dxk = 1; dxk < 4; ++dxk)
+                    umma_f16(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_lo + dxk * 2), idesc3, 1u);
+            } else if (s0 == 6) {
+                umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc1, 1u);
+                umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + 2 * kG), idesc1, 1u);
+#pragma unroll
+                for (int dxk = 1; dxk < 4; ++dxk) {
+                    const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
+                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc2, 1u);
+                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + 2 * kG), idesc1, 1u);
+                }
+            } else {
+                umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
+#pragma unroll
+                for (int dxk = 1; dxk < 4; ++dxk) {
+                    const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
+                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc1, 1u);
+                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + kG), idesc2, 1u);
+                }
+            }
+        };
+        auto issue_part2 = [&](uint32_t a_lo, int s0) {
+            const uint32_t d = tmem_base + s0 * NG;
+            if (s0 <= 5) {
+#pragma unroll
+                for (int dxk = 4; dxk < 12; ++dxk) {
+                    const int dx = dxk >> 2, k = dxk & 3;
+                    umma_f16(d, mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2), mk_desc(desc_hi, w_lo + dx * kDx + k * 2),
+                             idesc3, 1u);
+                }
+            } else if (s0 == 6) {
+#pragma unroll
+                for (int dxk = 4; dxk < 12; ++dxk) {
+                    const int dx = dxk >> 2, k = dxk & 3;
+                    const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
+                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
+                }
+            } else {
+#pragma unroll
+                for (int dxk = 4; dxk < 12; ++dxk) {
+                    const int dx = dxk >> 2, k = dxk & 3;
+                    const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
+                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
+                }
+            }
+        };
+        // Edge rows of a segment (first / last two input rows): one MMA per group and K-step.
+        auto edge_row = [&](int y, int ya, int yb, uint32_t i, int t0) {
+            const uint32_t stage = i % kStages, use = i / kStages;
+            const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
+            const int s0 = (-t0) & 7;
+            // group g (0..2) = vertical tap: input row y feeds output row y + 1 - g
+            const int g_lo = (y + 1 <= yb) ? 0 : ((y <= yb) ? 1 : 2);
+            const int g_hi = (y - 1 >= ya) ? 2 : ((y >= ya) ? 1 : 0);
+            // groups whose output row receives its first contribution from this input row
+            const int fresh_hi = (y == 0) ? g_hi : ((g_lo == 0) ? 0 : g_lo - 1);
+            for (int g = g_lo; g <= fresh_hi; ++g) {
+                const int tg = t0 - g;
+                mbar_wait(base + kBarAccEmpty + 8 * ((s0 + g) & 7), ((tg >> 3) & 1) ^ 1, dbg, TAG_ACC_EMPTY, tg);
+            }
+            mbar_wait(base + kBarAFull + 8 * stage, use & 1, dbg, TAG_A_FULL, i);
+            tc_fence_after();
+            if (elect_one()) {
+                for (int dxk = 0; dxk < 12; ++dxk) {
+                    const int dx = dxk >> 2, k = dxk & 3;
+                    const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                    for (int g = g_lo; g <= g_hi; ++g)
+                        umma_f16(tmem_base + ((s0 + g) & 7) * NG, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + g * kG),
+                                 idesc1, (dxk == 0 && g <= fresh_hi) ? 0u : 1u);
+                }
+                umma_commit(base + kBarAEmpty + 8 * stage);  // A slot reusable once these MMAs retire
+                if (g_hi == 2) umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));  // row y-1 complete
+                if (y == CH - 1 && yb == CH - 1)                                       // bottom edge: row y too
+                    umma_commit(base + kBarAccFull + 8 * ((s0 + 1) & 7));
+            }
+            __syncwarp();
+        };
+
         SegIter it(p);
         int strip, ya, yb;
-        uint32_t i = 0;
-        int t_base = 0;
-        bool prechecked = false;  // barriers of the current row were already observed during the previous row
+        uint32_t i = 0;   // input rows issued so far (ring stage = i mod kStages)
+        int t_base = 0;   // output rows of earlier segments
         while (it.next(strip, ya, yb)) {
             const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
-            for (int y = y_lo; y <= y_hi; ++y, ++i) {
-                const uint32_t stage = i & (kStages - 1), use = i / kStages;
-                const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
-                const int t0 = t_base + (y + 1 - ya);  // sequence number of output row y+1
-                const int s0 = (-t0) & 7;              // its TMEM slot; group g -> (s0 + g) & 7
-                const uint32_t bar_full = base + kBarAFull + 8 * stage;
-                if (y > ya && y < yb) {
-                    // ---- interior row: groups 0..2 enabled, only group 0 fresh, row y-1 completes.
-                    // The tensor pipe's instruction queue is shallow, so every cycle this thread spends
-                    // not issuing is a bubble: the barrier checks for row y+1 are made in the middle
-                    // of row y, while MMAs are queued.
+            int y = y_lo;
+            for (; y <= min(ya, y_hi); ++y, ++i) edge_row(y, ya, yb, i, t_base + (y + 1 - ya));
+            // ---- interior rows ya+1 .. yb-1: groups 0..2 enabled, only group 0 fresh, row y-1 completes.
+            // The tensor pipe's instruction queue is shallow: every cycle the issuing thread spends on
+            // anything else between two rows is a bubble.  So the barriers of row y+1 are polled in the
+            // middle of row y, and the loop carries only (i, t0).
+            int n_int = yb - ya - 1;
+            if (n_int > 0) {
+                int t0 = t_base + 2;  // y = ya + 1
+                {
+                    const int s0 = (-t0) & 7;
+                    mbar_wait(base + kBarAccEmpty + 8 * s0, ((t0 >> 3) & 1) ^ 1, dbg, TAG_ACC_EMPTY, t0);
+                    mbar_wait(base + kBarAFull + 8 * (i % kStages), (i / kStages) & 1, dbg, TAG_A_FULL, i);
+                    tc_fence_after();
+                }
+                const bool leader = elect_one();
+                for (; n_int > 0; --n_int, ++i, ++t0, ++y) {
+                    const uint32_t stage = i % kStages;
+                    const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
+                    const int s0 = (-t0) & 7;
                     long long* const tr = (p.trace && blockIdx.x == 0 && i < 256) ? p.trace + i * 4 : nullptr;
-                    if (tr && lane == 0) tr[0] = clock64();
-                    if (!prechecked) {
-                        const uint32_t bar_e = base + kBarAccEmpty + 8 * s0;
-                        const uint32_t par_e = ((t0 >> 3) & 1) ^ 1;
+                    if (tr && lane == 0) { tr[0] = clock64(); tr[3] = s0 << 4; }
+                    if (leader) issue_part1(a_lo, s0);
+                    // look ahead: barriers of the next interior row
+                    bool ok = true;
+                    uint32_t bar_e = 0, par_e = 0, bar_f = 0, par_f = 0;
+                    if (n_int > 1) {
+                        bar_e = base + kBarAccEmpty + 8 * ((s0 + 7) & 7);
+                        par_e = (((t0 + 1) >> 3) & 1) ^ 1;
+                        bar_f = base + kBarAFull + 8 * ((i + 1) % kStages);
+                        par_f = ((i + 1) / kStages) & 1;
                         const bool ok_e = mbar_try_wait(bar_e, par_e);
-                        const bool ok_f = mbar_try_wait(bar_full, use & 1);
-                        if (!ok_e) mbar_wait(bar_e, par_e, dbg, TAG_ACC_EMPTY, t0);
-                        if (!ok_f) mbar_wait(bar_full, use & 1, dbg, TAG_A_FULL, i);
-                        tc_fence_after();
+                        const bool ok_f = mbar_try_wait(bar_f, par_f);
+                        ok = ok_e && ok_f;
                     }
-                    if (tr && lane == 0) { tr[1] = clock64(); tr[3] = (prechecked ? 1 : 0) | (s0 << 4); }
-                    const uint64_t a0 = mk_desc(desc_hi, a_lo - 8);
-                    const uint32_t d = tmem_base + s0 * NG;
-                    // part 1: the first K-step (fresh group overwrites) and three more K-steps
-                    if (elect_one()) {
-                        if (s0 <= 5) {
-                            umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                            umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
-#pragma unroll
-                            for (int dxk = 1; dxk < 4; ++dxk)
-                                umma_f16(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_lo + dxk * 2), idesc3, 1u);
-                        } else if (s0 == 6) {
-                            umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                            umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc1, 1u);
-                            umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + 2 * kG), idesc1, 1u);
-#pragma unroll
-                            for (int dxk = 1; dxk < 4; ++dxk) {
-                                const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
-                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc2, 1u);
-                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + 2 * kG), idesc1, 1u);
-                            }
-                        } else {
-                            umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                            umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
-#pragma unroll
-                            for (int dxk = 1; dxk < 4; ++dxk) {
-                                const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
-                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc1, 1u);
-                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + kG), idesc2, 1u);
-                            }
-                        }
-                    }
-                    // look ahead: are the barriers of row y+1 (if it is interior too) already complete?
-                    prechecked = false;
-                    if (y + 1 < yb) {
-                        const uint32_t nstage = (i + 1) & (kStages - 1);
-                        const bool ok_e = mbar_try_wait(base + kBarAccEmpty + 8 * ((s0 + 7) & 7), (((t0 + 1) >> 3) & 1) ^ 1);
-                        const bool ok_f = mbar_try_wait(base + kBarAFull + 8 * nstage, ((i + 1) / kStages) & 1);
-                        if (ok_e && ok_f) {
-                            tc_fence_after();
-                            prechecked = true;
-                        }
-                    }
-                    // part 2: the remaining eight K-steps, then the commits
-                    if (elect_one()) {
-                        if (s0 <= 5) {
-#pragma unroll
-                            for (int dxk = 4; dxk < 12; ++dxk) {
-                                const int dx = dxk >> 2, k = dxk & 3;
-                                umma_f16(d, mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2),
-                                         mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc3, 1u);
-                            }
-                        } else if (s0 == 6) {
-#pragma unroll
-                            for (int dxk = 4; dxk < 12; ++dxk) {
-                                const int dx = dxk >> 2, k = dxk & 3;
-                                const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
-                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
-                            }
-                        } else {
-#pragma unroll
-                            for (int dxk = 4; dxk < 12; ++dxk) {
-                                const int dx = dxk >> 2, k = dxk & 3;
-                                const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                                umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
-                                umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
-                            }
-                        }
+                    if (tr && lane == 0) tr[1] = clock64();
+                    if (leader) {
+                        issue_part2(a_lo, s0);
                         umma_commit(base + kBarAEmpty + 8 * stage);
                         umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));
                     }
-                    __syncwarp();
-                    if (tr && lane == 0) tr[2] = clock64();
-                    continue;
-                }
-                prechecked = false;
-                // ---- edge rows of a segment (generic path)
-                // group g (0..2) = vertical tap: input row y feeds output row y + 1 - g
-                const int g_lo = (y + 1 <= yb) ? 0 : ((y <= yb) ? 1 : 2);
-                const int g_hi = (y - 1 >= ya) ? 2 : ((y >= ya) ? 1 : 0);
-                // groups whose output row receives its first contribution from this input row
-                const int fresh_hi = (y == 0) ? g_hi : ((g_lo == 0) ? 0 : g_lo - 1);
-                for (int g = g_lo; g <= fresh_hi; ++g) {
-                    const int tg = t0 - g;
-                    mbar_wait(base + kBarAccEmpty + 8 * ((s0 + g) & 7), ((tg >> 3) & 1) ^ 1, dbg, TAG_ACC_EMPTY, tg);
-                }
-                mbar_wait(bar_full, use & 1, dbg, TAG_A_FULL, i);
-                tc_fence_after();
-                if (elect_one()) {
-                    // one MMA per group and K-step: simple, and these rows are rare
-                    for (int dxk = 0; dxk < 12; ++dxk) {
-                        const int dx = dxk >> 2, k = dxk & 3;
-                        const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                        for (int g = g_lo; g <= g_hi; ++g)
-                            umma_f16(tmem_base + ((s0 + g) & 7) * NG, ad,
-                                     mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + g * kG), idesc1,
-                                     (dxk == 0 && g <= fresh_hi) ? 0u : 1u);
+                    if (!ok) {
+                        mbar_wait(bar_e, par_e, dbg, TAG_ACC_EMPTY, t0 + 1);
+                        mbar_wait(bar_f, par_f, dbg, TAG_A_FULL, i + 1);
                     }
-                    umma_commit(base + kBarAEmpty + 8 * stage);  // A slot reusable once these MMAs retire
-                    if (g_hi == 2) umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));  // row y-1 complete
-                    if (y == CH - 1 && yb == CH - 1)                                       // bottom edge: row y too
-                        umma_commit(base + kBarAccFull + 8 * ((s0 + 1) & 7));
+                    tc_fence_after();
+                    if (tr && lane == 0) tr[2] = clock64();
                 }
                 __syncwarp();
             }
+            for (; y <= y_hi; ++y, ++i) edge_row(y, ya, yb, i, t_base + (y + 1 - ya));
             t_base += yb - ya + 1;
         }
     } else {
@@ -360,33 +384,34 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if (p.flags & 64u) continue;  // timing experiment: drain only
 
                 if constexpr (!TAIL) {
-                    if (inside && !(p.flags & 16u)) {  // flag 16: timing experiment without the stores
-                        const bool keep = colok && (p.rowflag[pr] != 0);
-                        uint8_t* const orow = reinterpret_cast<uint8_t*>(p.out) +
-                                              (static_cast<long long>(pr) * p.canvas_w + cx) * 128;
-                        const float4* const sb = reinterpret_cast<const float4*>(base_ptr + kOffBias);
-                        const float4* const ss = reinterpret_cast<const float4*>(base_ptr + kOffSlope);
+                    const bool keep = colok && (p.rowflag[pr] != 0);
+                    const uint32_t stg = base + kOffStage + grp * kRowBytes;
+                    const bool gleader = (q == 0 && lane == 0);
+                    if (gleader) bulk_wait_read<0>();   // this group's previous row has left the staging buffer
+                    named_bar_sync(1 + grp, 128);
+                    if (m >= 1 && m <= kStripPx) {
+                        const int row = m - 1;
+                        const uint32_t rbase = stg + row * 128;
 #pragma unroll
-                        for (int c16 = 0; c16 < 4; ++c16) {
-                            uint32_t pk[8];
+                        for (int c8 = 0; c8 < 8; ++c8) {
+                            uint32_t pk[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const int ch = c16 * 16 + j * 4;
-                                const float4 b4 = sb[ch >> 2], a4 = ss[ch >> 2];
-                                float v0 = __uint_as_float(acc[ch]) + b4.x;
-                                float v1 = __uint_as_float(acc[ch + 1]) + b4.y;
-                                float v2 = __uint_as_float(acc[ch + 2]) + b4.z;
-                                float v3 = __uint_as_float(acc[ch + 3]) + b4.w;
-                                v0 = fmaxf(v0, 0.f) + a4.x * fminf(v0, 0.f);
-                                v1 = fmaxf(v1, 0.f) + a4.y * fminf(v1, 0.f);
-                                v2 = fmaxf(v2, 0.f) + a4.z * fminf(v2, 0.f);
-                                v3 = fmaxf(v3, 0.f) + a4.w * fminf(v3, 0.f);
-                                pk[2 * j] = keep ? pack_half2(v0, v1) : 0u;
-                                pk[2 * j + 1] = keep ? pack_half2(v2, v3) : 0u;
+                                const int ch = c8 * 8 + j * 2;
+                                float v0 = __uint_as_float(acc[ch]) + p.bias[ch];
+                                float v1 = __uint_as_float(acc[ch + 1]) + p.bias[ch + 1];
+                                v0 = fmaxf(v0, 0.f) + p.slope[ch] * fminf(v0, 0.f);
+                                v1 = fmaxf(v1, 0.f) + p.slope[ch + 1] * fminf(v1, 0.f);
+                                pk[j] = keep ? pack_half2(v0, v1) : 0u;
                             }
-                            if (p.flags & 4u) st_global_v8_hint(orow + c16 * 32, pk, kPolicyEvictLast);
-                            else st_global_v8(orow + c16 * 32, pk);
+                            st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                         }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + grp, 128);
+                    if (gleader) {
+                        tma_store_3d(&out_map, stg, 0, x0, pr);
+                        bulk_commit();
                     }
                 } else {
                     constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
@@ -419,6 +444,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         }
     }
 
+    if (!TAIL && warp >= 2 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -428,9 +454,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     }
 }
 
-template <int NG>
+template <int NG, bool TAIL>
 constexpr size_t smem_bytes_t() {
-    return 1024 /*alignment slack*/ + kCtrlBytes + w_bytes(NG) + kGuard + kStages * kRowBytes + kGuard;
+    return 1024 /*alignment slack*/ + kCtrlBytes + w_bytes(NG) + kGuard + kStages * kRowBytes + kGuard +
+           (TAIL ? 0 : 2 * kRowBytes);
 }
 
 }  // namespace
@@ -459,29 +486,30 @@ void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16
 cudaError_t conv_kernels_init() {
     cudaError_t e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<64>()));
+                             static_cast<int>(smem_bytes_t<64, false>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<16>()));
+                             static_cast<int>(smem_bytes_t<16, true>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<32>()));
+                             static_cast<int>(smem_bytes_t<32, true>()));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(conv3x3_umma_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<48>()));
+                             static_cast<int>(smem_bytes_t<48, true>()));
     return e;
 }
 
-cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const ConvParams& p) {
-    conv3x3_umma_kernel<64, false><<<grid, kConvThreads, smem_bytes_t<64>(), st>>>(in_map, p);
+cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
+                             const ConvParams& p) {
+    conv3x3_umma_kernel<64, false><<<grid, kConvThreads, smem_bytes_t<64, false>(), st>>>(in_map, out_map, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p) {
     switch (scale) {
-        case 2: conv3x3_umma_kernel<16, true><<<grid, kConvThreads, smem_bytes_t<16>(), st>>>(in_map, p); break;
-        case 3: conv3x3_umma_kernel<32, true><<<grid, kConvThreads, smem_bytes_t<32>(), st>>>(in_map, p); break;
-        case 4: conv3x3_umma_kernel<48, true><<<grid, kConvThreads, smem_bytes_t<48>(), st>>>(in_map, p); break;
+        case 2: conv3x3_umma_kernel<16, true><<<grid, kConvThreads, smem_bytes_t<16, true>(), st>>>(in_map, in_map, p); break;
+        case 3: conv3x3_umma_kernel<32, true><<<grid, kConvThreads, smem_bytes_t<32, true>(), st>>>(in_map, in_map, p); break;
+        case 4: conv3x3_umma_kernel<48, true><<<grid, kConvThreads, smem_bytes_t<48, true>(), st>>>(in_map, in_map, p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -10,7 +10,7 @@ namespace reve {
 
 constexpr int kBoxPx = 128;    // pixels per TMA row box = UMMA M
 constexpr int kStripPx = 126;  // valid output pixels per strip row (box minus the 2 halo columns)
-constexpr int kStages = 8;     // A-row ring depth
+constexpr int kStages = 7;     // A-row ring depth
 constexpr int kConvThreads = 320;  // producer warp + MMA warp + 2 x 4 epilogue warps
 
 // Parameters of the tcgen05 3x3 convolution kernels (body: 64->64 + PReLU -> fp16 canvas;
@@ -25,7 +25,7 @@ struct ConvParams {
     const void* weights;        // pre-swizzled B operand blob of this layer (global memory)
     __half* out;                // body: output canvas [canvas_h][canvas_w][64] fp16
     int reverse;                // sweep the strip-rows bottom-up (weights blob packed accordingly)
-    uint32_t flags;             // debug: bit1 = no evict-first on loads, bit2 = evict-last on stores
+    uint32_t flags;             // debug/timing experiments: bit1 = no evict-first on loads, 8/32/64 = ablations
     DebugBlock* dbg;            // mapped pinned host memory, may be null
     long long* trace;           // debug timeline of CTA 0 (device memory, may be null)
     // tail only
@@ -40,16 +40,17 @@ struct ConvParams {
     float slope[64];
 };
 
-// First convolution (3 -> 64) + PReLU on CUDA cores, fused with the u8 -> float unpack, the
-// reflect-101 pre-pad gather and the canvas layout; weights live in the constant bank.
+// First convolution (3 -> 64) + PReLU on tensor cores (K = 27 padded to 32), fused with the u8 -> fp16
+// unpack, the reflect-101 pre-pad gather and the canvas layout (conv0.cu).
 struct Conv0Params {
     int canvas_w, canvas_h;
     const uint8_t* src;
     long long src_stride;
     const int* src_x;
     const int* src_y;
-    __half* dst;               // canvas [canvas_h][canvas_w][64] fp16
-    float w[27][64];           // [(ky*3 + kx)*3 + c][co]
+    const void* weights;       // B operand blob (pack_conv0_weights)
+    DebugBlock* dbg;
+    uint32_t flags;
     float bias[64];
     float slope[64];
 };
@@ -60,8 +61,11 @@ size_t conv_weight_blob_bytes(int ng);
 void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16_t* blob);
 
 cudaError_t conv_kernels_init();  // opt-in shared memory attributes; call once per device
-cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const ConvParams& p);
+cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p);
-cudaError_t launch_conv0(cudaStream_t st, const Conv0Params& p);
+size_t conv0_weight_blob_bytes();
+void pack_conv0_weights(const float* w_oihw, uint16_t* blob);
+cudaError_t conv0_kernel_init();
+cudaError_t launch_conv0(cudaStream_t st, int grid, const CUtensorMap& out_map, const Conv0Params& p);
 
 }  // namespace reve
