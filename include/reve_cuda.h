@@ -87,7 +87,9 @@ int reve_host_alloc(size_t bytes, void** out);
 void reve_host_free(void* p);
 
 /* Asynchronous frame: H2D copy -> kernels -> D2H copy on the context's streams.  The caller keeps
- * rgb_in / rgb_out valid until the matching reve_wait.  Strides in bytes (>= 3*w). */
+ * rgb_in / rgb_out valid until the matching reve_wait.  Strides in bytes (>= 3*w).  Kernels run on
+ * batches of up to 4 frames (stacked on one canvas): the copy starts at once, the kernels are
+ * enqueued when a batch is full or when reve_wait / reve_sync needs a frame of a partial batch. */
 int reve_submit(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, uint8_t* rgb_out,
                 size_t out_stride, uint64_t tag);
 /* Blocks until the oldest submitted frame is complete (FIFO) and returns its tag. */
@@ -107,7 +109,9 @@ typedef struct reve_profile {
     uint64_t launches_conv0, launches_body, launches_tail; /* kernels launched since reset */
     double ms_conv0, ms_body, ms_tail; /* summed CUDA-event time; only while profiling is on */
     uint64_t timed_body;               /* body launches covered by ms_body */
-    uint64_t timed_frames;
+    uint64_t timed_frames;             /* tail launches (= batches) covered by the timings */
+    uint64_t frames;                   /* frames enqueued since reset */
+    uint64_t body_frames;              /* sum over body launches of the frames each one processed */
 } reve_profile;
 /* on != 0: bracket every kernel launch with CUDA events (slower; for roofline measurements). */
 int reve_ctx_set_profiling(reve_ctx* ctx, int on);

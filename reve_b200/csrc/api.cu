@@ -32,6 +32,8 @@ struct Slot {
     uint8_t* d_out = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_done = nullptr;
     uint64_t tag = 0;
+    uint8_t* host_out = nullptr;   // destination of the D2H copy issued when the batch is flushed
+    size_t host_out_stride = 0;
 };
 
 struct ProfEvent {
@@ -50,12 +52,15 @@ struct reve_ctx {
     __half* act[2] = {nullptr, nullptr};
     size_t act_bytes = 0;
     uint8_t *d_colflag = nullptr, *d_rowflag = nullptr;
-    int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr;
+    int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr, *d_rowframe = nullptr;
+    int batch = 1;        // frames stacked on the canvas per launch set (<= kMaxBatch)
+    int frame_ch = 0;     // canvas rows of one frame (frames are frame_ch + 1 rows apart: one gap row)
+    int n_strips = 0;
+    std::vector<int> pending;  // ring slots whose H2D copy is issued but whose kernels are not yet enqueued
     void* d_wblob[kNumConv] = {};  // per layer: forward-sweep blob followed by the reverse-sweep blob
     CUtensorMap map_in[2], map_out[2];
     CUtensorMap map_flat0;   // act[0] as a flat [pixels][64] tensor (conv0 output tiles of 128 pixels)
     void* d_w0 = nullptr;    // conv0 B operand
-    int grid0 = 0;
     Conv0Params c0;
     ConvParams body[kNumBody];
     ConvParams tail;
@@ -127,31 +132,75 @@ void prof_mark(reve_ctx* ctx, int kind) {
     ctx->prof_events.push_back({kind, ev});
 }
 
-// Enqueue the 18 launches of one frame on the compute stream.
-int enqueue_frame(reve_ctx* ctx, const uint8_t* d_in, long long in_stride, uint8_t* d_out, long long out_stride,
-                  int stop_after_layers = kNumConv) {
+// Enqueue the 18 launches of one batch (n <= ctx->batch frames stacked on the canvas, separated by
+// gap rows) on the compute stream.
+int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in_stride, uint8_t* const* d_out,
+                  long long out_stride, int stop_after_layers = kNumConv) {
+    const int ch = n * (ctx->frame_ch + 1) - 1;   // active canvas rows (the trailing gap row is excluded)
+    const long long total = static_cast<long long>(ctx->n_strips) * ch;
+    const int grid = static_cast<int>(total < ctx->grid ? total : ctx->grid);
     prof_mark(ctx, -1);
     Conv0Params c0 = ctx->c0;
-    c0.src = d_in;
+    c0.canvas_h = ch;
+    for (int f = 0; f < n; ++f) c0.src[f] = d_in[f];
     c0.src_stride = in_stride;
-    CK(ctx, launch_conv0(ctx->s_comp, ctx->grid0, ctx->map_flat0, c0));
+    {
+        const long long tiles0 = (static_cast<long long>(c0.canvas_w) * ch + 127) / 128;
+        CK(ctx, launch_conv0(ctx->s_comp, static_cast<int>(tiles0 < ctx->sm_count ? tiles0 : ctx->sm_count), ctx->map_flat0, c0));
+    }
     ctx->prof.launches_conv0++;
     prof_mark(ctx, 0);
     for (int k = 0; k < kNumBody && k + 1 < stop_after_layers; ++k) {
-        CK(ctx, launch_conv_body(ctx->s_comp, ctx->grid, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], ctx->body[k]));
+        ConvParams b = ctx->body[k];
+        b.canvas_h = ch;
+        b.total_rows = static_cast<int>(total);
+        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], b));
         ctx->prof.launches_body++;
+        ctx->prof.body_frames += n;
         prof_mark(ctx, 1);
     }
     if (stop_after_layers >= kNumConv) {
         ConvParams t = ctx->tail;
-        t.src = d_in;
+        t.canvas_h = ch;
+        t.total_rows = static_cast<int>(total);
+        for (int f = 0; f < n; ++f) {
+            t.src[f] = d_in[f];
+            t.dst[f] = d_out[f];
+        }
         t.src_stride = in_stride;
-        t.dst = d_out;
         t.dst_stride = out_stride;
-        CK(ctx, launch_conv_tail(ctx->s_comp, ctx->grid, ctx->scale, ctx->map_in[0], t));
+        CK(ctx, launch_conv_tail(ctx->s_comp, grid, ctx->scale, ctx->map_in[0], t));
         ctx->prof.launches_tail++;
         prof_mark(ctx, 2);
     }
+    ctx->prof.frames += n;
+    return REVE_OK;
+}
+
+// Kernels + D2H copies for every submitted frame whose compute is still pending.
+int flush_pending(reve_ctx* ctx) {
+    if (ctx->pending.empty()) return REVE_OK;
+    const int n = static_cast<int>(ctx->pending.size());
+    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3, out_row = in_row * ctx->scale;
+    const uint8_t* ins[kMaxBatch];
+    uint8_t* outs[kMaxBatch];
+    for (int f = 0; f < n; ++f) {
+        Slot& s = ctx->ring[ctx->pending[f]];
+        ins[f] = s.d_in;
+        outs[f] = s.d_out;
+        CK(ctx, cudaStreamWaitEvent(ctx->s_comp, s.ev_h2d, 0));
+    }
+    int rc = enqueue_batch(ctx, n, ins, static_cast<long long>(in_row), outs, static_cast<long long>(out_row));
+    if (rc != REVE_OK) return rc;
+    const int out_h = ctx->g.in_h * ctx->scale;
+    CK(ctx, cudaEventRecord(ctx->ring[ctx->pending[0]].ev_comp, ctx->s_comp));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ring[ctx->pending[0]].ev_comp, 0));
+    for (int f = 0; f < n; ++f) {
+        Slot& s = ctx->ring[ctx->pending[f]];
+        CK(ctx, cudaMemcpy2DAsync(s.host_out, s.host_out_stride, s.d_out, out_row, out_row, out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(ctx, cudaEventRecord(s.ev_done, ctx->s_d2h));
+    }
+    ctx->pending.clear();
     return REVE_OK;
 }
 
@@ -193,6 +242,7 @@ void destroy_ctx(reve_ctx* ctx) {
     cudaFree(ctx->d_srcy);
     cudaFree(ctx->d_outx);
     cudaFree(ctx->d_outy);
+    cudaFree(ctx->d_rowframe);
     for (void* p : ctx->d_wblob) cudaFree(p);
     cudaFree(ctx->d_w0);
     cudaFree(ctx->d_trace);
@@ -219,7 +269,6 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     int rc = make_geometry(in_w, in_h, m.scale, tile, prepad, ctx->g, gerr);
     if (rc != REVE_OK) return set_err(ctx, rc, gerr);
     const Geometry& g = ctx->g;
-    const int cw = g.canvas_w(), ch = g.canvas_h();
 
     CK(ctx, conv_kernels_init());
     CK(ctx, conv0_kernel_init());
@@ -230,16 +279,38 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     std::memset(ctx->dbg_host, 0, sizeof(DebugBlock));
     CK(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->dbg_dev), ctx->dbg_host, 0));
 
-    // geometry tables
+    // batch size: frames stacked vertically on one canvas (one zero gap row between frames), bounded by
+    // kMaxBatch, the ring depth and ~6 GB of activation memory
+    const int fch = g.canvas_h();
+    const int cw = g.canvas_w();
+    ctx->frame_ch = fch;
+    ctx->batch = kMaxBatch < ring_depth ? kMaxBatch : ring_depth;
+    while (ctx->batch > 1 && 2.0 * cw * (static_cast<double>(ctx->batch) * (fch + 1)) * 128.0 > 6e9) --ctx->batch;
+    if (const char* be = std::getenv("REVE_DEBUG_BATCH")) {
+        const int b = std::atoi(be);
+        if (b >= 1 && b < ctx->batch) ctx->batch = b;
+    }
+    const int ch = ctx->batch * (fch + 1) - 1;   // canvas rows allocated
+
+    // geometry tables (y tables repeated per stacked frame)
     std::vector<uint8_t> colflag(cw), rowflag(ch);
+    std::vector<int> srcy(ch), outy(ch), rowframe(ch);
     for (int i = 0; i < cw; ++i) colflag[i] = g.x.src[i] >= 0;
-    for (int i = 0; i < ch; ++i) rowflag[i] = g.y.src[i] >= 0;
+    for (int r = 0; r < ch; ++r) {
+        const int f = r / (fch + 1), i = r % (fch + 1);
+        const bool gap = (i == fch);
+        srcy[r] = gap ? -1 : g.y.src[i];
+        outy[r] = gap ? -1 : g.y.out[i];
+        rowframe[r] = (gap || g.y.src[i] < 0) ? -1 : f;
+        rowflag[r] = srcy[r] >= 0;
+    }
     if ((rc = upload(ctx, &ctx->d_colflag, colflag.data(), cw))) return rc;
     if ((rc = upload(ctx, &ctx->d_rowflag, rowflag.data(), ch))) return rc;
     if ((rc = upload(ctx, &ctx->d_srcx, g.x.src.data(), sizeof(int) * cw))) return rc;
-    if ((rc = upload(ctx, &ctx->d_srcy, g.y.src.data(), sizeof(int) * ch))) return rc;
+    if ((rc = upload(ctx, &ctx->d_srcy, srcy.data(), sizeof(int) * ch))) return rc;
     if ((rc = upload(ctx, &ctx->d_outx, g.x.out.data(), sizeof(int) * cw))) return rc;
-    if ((rc = upload(ctx, &ctx->d_outy, g.y.out.data(), sizeof(int) * ch))) return rc;
+    if ((rc = upload(ctx, &ctx->d_outy, outy.data(), sizeof(int) * ch))) return rc;
+    if ((rc = upload(ctx, &ctx->d_rowframe, rowframe.data(), sizeof(int) * ch))) return rc;
 
     // activation canvases (ping-pong), zero-initialised
     ctx->act_bytes = static_cast<size_t>(cw) * ch * 64 * sizeof(__half);
@@ -297,6 +368,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     c0.canvas_h = ch;
     c0.src_x = ctx->d_srcx;
     c0.src_y = ctx->d_srcy;
+    c0.row_frame = ctx->d_rowframe;
     c0.weights = ctx->d_w0;
     c0.dbg = ctx->dbg_dev;
     c0.flags = dflags;
@@ -304,13 +376,10 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         c0.bias[co] = m.conv[0].b[co];
         c0.slope[co] = m.conv[0].slope[co];
     }
-    {
-        const long long tiles0 = (static_cast<long long>(cw) * ch + 127) / 128;
-        ctx->grid0 = static_cast<int>(tiles0 < ctx->sm_count ? tiles0 : ctx->sm_count);
-    }
     const int n_strips = (cw + kStripPx - 1) / kStripPx;
+    ctx->n_strips = n_strips;
     const long long total = static_cast<long long>(n_strips) * ch;
-    ctx->grid = static_cast<int>(total < ctx->sm_count ? total : ctx->sm_count);
+    ctx->grid = ctx->sm_count;   // persistent: one CTA per SM (clamped to the work of a batch at launch)
     // Debug knob (tests only): cap the persistent grid so one CTA walks many rows / strips.
     if (const char* ge = std::getenv("REVE_DEBUG_GRID")) {
         const int gcap = std::atoi(ge);
@@ -338,6 +407,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         p.src_y = ctx->d_srcy;
         p.out_x = ctx->d_outx;
         p.out_y = ctx->d_outy;
+        p.row_frame = ctx->d_rowframe;
         const ConvLayer& L = m.conv[k + 1];
         for (int c = 0; c < L.out_ch; ++c) {
             p.bias[c] = L.b[c];
@@ -524,25 +594,29 @@ int reve_submit(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, uint8_t*
     if (ctx->inflight == static_cast<int>(ctx->ring.size())) return set_err(ctx, REVE_E_BUSY, "submit ring full: call reve_wait");
     CK(ctx, cudaSetDevice(ctx->device));
     Slot& s = ctx->ring[ctx->head];
-    const int in_h = ctx->g.in_h, out_h = in_h * ctx->scale;
-    CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, in_h, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, ctx->g.in_h, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(ctx, cudaEventRecord(s.ev_h2d, ctx->s_h2d));
-    CK(ctx, cudaStreamWaitEvent(ctx->s_comp, s.ev_h2d, 0));
-    int rc = enqueue_frame(ctx, s.d_in, static_cast<long long>(in_row), s.d_out, static_cast<long long>(out_row));
-    if (rc != REVE_OK) return rc;
-    CK(ctx, cudaEventRecord(s.ev_comp, ctx->s_comp));
-    CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, s.ev_comp, 0));
-    CK(ctx, cudaMemcpy2DAsync(rgb_out, out_stride, s.d_out, out_row, out_row, out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CK(ctx, cudaEventRecord(s.ev_done, ctx->s_d2h));
     s.tag = tag;
+    s.host_out = rgb_out;
+    s.host_out_stride = out_stride;
+    ctx->pending.push_back(ctx->head);
     ctx->head = (ctx->head + 1) % static_cast<int>(ctx->ring.size());
     ctx->inflight++;
+    // kernels run on whole batches: enqueue once `batch` frames are pending (reve_wait / reve_sync flush the rest)
+    if (static_cast<int>(ctx->pending.size()) >= ctx->batch) return flush_pending(ctx);
     return REVE_OK;
 }
 
 int reve_wait(reve_ctx* ctx, uint64_t* tag) {
     if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
     if (ctx->inflight == 0) return set_err(ctx, REVE_E_EMPTY, "nothing in flight");
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (int slot : ctx->pending)
+        if (slot == ctx->oldest) {   // the oldest frame sits in a partial batch: run it now
+            int rc = flush_pending(ctx);
+            if (rc != REVE_OK) return rc;
+            break;
+        }
     Slot& s = ctx->ring[ctx->oldest];
     ctx->oldest = (ctx->oldest + 1) % static_cast<int>(ctx->ring.size());
     ctx->inflight--;
@@ -554,6 +628,10 @@ int reve_wait(reve_ctx* ctx, uint64_t* tag) {
 int reve_sync(reve_ctx* ctx) {
     if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
+    {
+        int rc = flush_pending(ctx);
+        if (rc != REVE_OK) return rc;
+    }
     CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
@@ -566,9 +644,15 @@ int reve_upscale_device(reve_ctx* ctx, const void* d_in, void* d_out, int n_fram
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3, out_row = in_row * ctx->scale;
     const size_t in_bytes = in_row * ctx->g.in_h, out_bytes = out_row * ctx->g.in_h * ctx->scale;
-    for (int f = 0; f < n_frames; ++f) {
-        int rc = enqueue_frame(ctx, static_cast<const uint8_t*>(d_in) + f * in_bytes, static_cast<long long>(in_row),
-                               static_cast<uint8_t*>(d_out) + f * out_bytes, static_cast<long long>(out_row));
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->batch) {
+        const int n = (n_frames - f0 < ctx->batch) ? n_frames - f0 : ctx->batch;
+        const uint8_t* ins[kMaxBatch];
+        uint8_t* outs[kMaxBatch];
+        for (int f = 0; f < n; ++f) {
+            ins[f] = static_cast<const uint8_t*>(d_in) + static_cast<size_t>(f0 + f) * in_bytes;
+            outs[f] = static_cast<uint8_t*>(d_out) + static_cast<size_t>(f0 + f) * out_bytes;
+        }
+        int rc = enqueue_batch(ctx, n, ins, static_cast<long long>(in_row), outs, static_cast<long long>(out_row));
         if (rc != REVE_OK) return rc;
     }
     return REVE_OK;
@@ -611,7 +695,9 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
     CK(ctx, cudaSetDevice(ctx->device));
     Slot& s = ctx->ring[0];
     CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, ctx->g.in_h, cudaMemcpyHostToDevice, ctx->s_comp));
-    int rc = enqueue_frame(ctx, s.d_in, static_cast<long long>(in_row), s.d_out, static_cast<long long>(in_row) * ctx->scale, layer);
+    const uint8_t* ins[1] = {s.d_in};
+    uint8_t* outs[1] = {s.d_out};
+    int rc = enqueue_batch(ctx, 1, ins, static_cast<long long>(in_row), outs, static_cast<long long>(in_row) * ctx->scale, layer);
     if (rc != REVE_OK) return rc;
     std::vector<__half> h(n);
     CK(ctx, cudaMemcpyAsync(h.data(), ctx->act[(layer - 1) & 1], n * sizeof(__half), cudaMemcpyDeviceToHost, ctx->s_comp));

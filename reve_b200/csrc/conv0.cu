@@ -101,14 +101,18 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         tmem_relinquish();
     }
     const int CW = p.canvas_w, CHh = p.canvas_h;
-    const bool tab_smem = (CW + CHh) <= kMaxTableInts;
+    const bool tab_smem = (CW + 2 * CHh) <= kMaxTableInts;
     int* const tab = reinterpret_cast<int*>(base_ptr + kOffTab);
     if (tab_smem) {
         for (int i = threadIdx.x; i < CW; i += kThreads) tab[i] = p.src_x[i];
-        for (int i = threadIdx.x; i < CHh; i += kThreads) tab[CW + i] = p.src_y[i];
+        for (int i = threadIdx.x; i < CHh; i += kThreads) {
+            tab[CW + i] = p.src_y[i];
+            tab[CW + CHh + i] = p.row_frame[i];
+        }
     }
     const int* const tx = tab_smem ? tab : p.src_x;
     const int* const ty = tab_smem ? tab + CW : p.src_y;
+    const int* const tf = tab_smem ? tab + CW + CHh : p.row_frame;
     if (warp == kFirstEpiWarp && lane == 0) {
         prefetch_tmap(&out_map);
         mbar_arrive_expect_tx(base + kBarW, kWBytes0);
@@ -141,14 +145,15 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
                         const int yy = cy + ky - 1;
-                        const int sy = (yy >= 0 && yy < CHh) ? ty[yy] : -1;
+                        const int sy = (yy >= 0 && yy < CHh) ? ty[yy] : -1;   // -1 across a frame/tile gap
+                        const uint8_t* const fsrc = p.src[max(tf[cy], 0)];
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
                             const int xx = cx + kx - 1;
                             const int sx = (xx >= 0 && xx < CW) ? tx[xx] : -1;
                             const int t = (ky * 3 + kx) * 3;
                             if (sy >= 0 && sx >= 0) {
-                                const uint8_t* s = p.src + static_cast<long long>(sy) * p.src_stride + sx * 3;
+                                const uint8_t* s = fsrc + static_cast<long long>(sy) * p.src_stride + sx * 3;
                                 v[t] = s[0];
                                 v[t + 1] = s[1];
                                 v[t + 2] = s[2];

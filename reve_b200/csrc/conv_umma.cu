@@ -149,7 +149,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         if (lane == 0) {
             mbar_arrive_expect_tx(base + kBarW, kWBytes);
             bulk_load_1d(base + kOffW, p.weights, kWBytes, base + kBarW);
-            const uint64_t policy = (p.flags & 2u) ? kPolicyEvictNormal : kPolicyEvictFirst;
+            const uint64_t policy = kPolicyEvictFirst;  // activations are read once per layer
             SegIter it(p);
             int strip, ya, yb;
             uint32_t i = 0;
@@ -159,10 +159,6 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 for (int y = y_lo; y <= y_hi; ++y, ++i) {
                     const uint32_t stage = i % kStages, use = i / kStages;
                     mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
-                    if (p.flags & 32u) {  // timing experiment: no TMA traffic
-                        mbar_arrive(base + kBarAFull + 8 * stage);
-                        continue;
-                    }
                     mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
                     tma_load_3d_hint(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage, 0,
                                      x0 - 1, rev ? CH - 1 - y : y, policy);
@@ -325,11 +321,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));
                     }
                     if (!ok) {
+                        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[2040] += 1;   // look-ahead misses
                         mbar_wait(bar_e, par_e, dbg, TAG_ACC_EMPTY, t0 + 1);
                         mbar_wait(bar_f, par_f, dbg, TAG_A_FULL, i + 1);
                     }
                     tc_fence_after();
                     if (tr && lane == 0) tr[2] = clock64();
+                    if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[2041] += 1;       // interior rows
                 }
                 __syncwarp();
             }
@@ -366,22 +364,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if (tr) tr[1] = clock64();
                 tc_fence_after();
                 uint32_t acc[NG];
-                if (p.flags & 8u) {  // timing experiment: no TMEM reads
 #pragma unroll
-                    for (int c = 0; c < NG; ++c) acc[c] = c + t;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < NG / 16; ++c) {
-                        uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
-                        tmem_ld16(tmem_lane + s * NG + c * 16, dst);
-                    }
+                for (int c = 0; c < NG / 16; ++c) {
+                    uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
+                    tmem_ld16(tmem_lane + s * NG + c * 16, dst);
                 }
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(base + kBarAccEmpty + 8 * s);
                 if (tr) tr[2] = clock64();
-                if (p.flags & 64u) continue;  // timing experiment: drain only
 
                 if constexpr (!TAIL) {
                     const bool keep = colok && (p.rowflag[pr] != 0);
@@ -417,12 +409,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
                     const int oy = p.out_y[pr];
                     if (ox >= 0 && oy >= 0) {
-                        const uint8_t* sp = p.src + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
+                        const int fr = p.row_frame[pr];
+                        const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
                         const float xin[3] = {static_cast<float>(sp[0]), static_cast<float>(sp[1]),
                                               static_cast<float>(sp[2])};
 #pragma unroll
                         for (int i = 0; i < S; ++i) {
-                            uint8_t* dp = p.dst + static_cast<long long>(oy * S + i) * p.dst_stride +
+                            uint8_t* dp = p.dst[fr] + static_cast<long long>(oy * S + i) * p.dst_stride +
                                           static_cast<long long>(ox) * (S * 3);
 #pragma unroll
                             for (int j = 0; j < S; ++j) {

@@ -11,6 +11,7 @@ namespace reve {
 constexpr int kBoxPx = 128;    // pixels per TMA row box = UMMA M
 constexpr int kStripPx = 126;  // valid output pixels per strip row (box minus the 2 halo columns)
 constexpr int kStages = 7;     // A-row ring depth
+constexpr int kMaxBatch = 4;    // frames stacked on one canvas per launch (gap row between frames)
 constexpr int kConvThreads = 320;  // producer warp + MMA warp + 2 x 4 epilogue warps
 
 // Parameters of the tcgen05 3x3 convolution kernels (body: 64->64 + PReLU -> fp16 canvas;
@@ -29,8 +30,9 @@ struct ConvParams {
     DebugBlock* dbg;            // mapped pinned host memory, may be null
     long long* trace;           // debug timeline of CTA 0 (device memory, may be null)
     // tail only
-    const uint8_t* src;         // u8 RGB input frame (device)
-    uint8_t* dst;               // u8 RGB output frame (device)
+    const uint8_t* src[kMaxBatch];  // u8 RGB input frames of the batch (device)
+    uint8_t* dst[kMaxBatch];        // u8 RGB output frames (device)
+    const int* row_frame;       // [canvas_h] frame of the batch a canvas row belongs to (-1 = gap)
     long long src_stride, dst_stride;
     const int* src_x;           // [canvas_w] source column (or -1)
     const int* src_y;           // [canvas_h]
@@ -44,10 +46,11 @@ struct ConvParams {
 // unpack, the reflect-101 pre-pad gather and the canvas layout (conv0.cu).
 struct Conv0Params {
     int canvas_w, canvas_h;
-    const uint8_t* src;
+    const uint8_t* src[kMaxBatch];
     long long src_stride;
     const int* src_x;
     const int* src_y;
+    const int* row_frame;      // [canvas_h] frame of the batch (-1 = gap row)
     const void* weights;       // B operand blob (pack_conv0_weights)
     DebugBlock* dbg;
     uint32_t flags;

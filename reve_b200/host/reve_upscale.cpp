@@ -160,7 +160,8 @@ int main(int argc, char** argv) {
         closedir(d);
     } else { std::fprintf(stderr, "error: cannot open input directory %s\n", o.in.c_str()); return 1; }
     std::sort(names.begin(), names.end());
-    mkdir(o.out.c_str(), 0777);
+    for (size_t pos = 1; pos <= o.out.size(); ++pos)   // mkdir -p (the reference creates only the leaf, lib.rs:130-132)
+        if (pos == o.out.size() || o.out[pos] == '/') mkdir(o.out.substr(0, pos).c_str(), 0777);
     if (names.empty()) return 0;
 
     // upstream appends "-x<scale>" only to the bare name; reve passes "...-x2" whatever -s is (lib.rs:141)

@@ -170,7 +170,8 @@ def test_device_resident_path_matches_submit_path():
         for i in range(n):
             assert np.array_equal(dev[i], up.upscale(frames[i]))
         prof = up.profile()
-        assert prof["launches_body"] == 16 * 2 * n and prof["launches_conv0"] == 2 * n and prof["launches_tail"] == 2 * n
+        assert prof["frames"] == 2 * n and prof["body_frames"] == 16 * 2 * n
+        assert prof["launches_body"] == 16 * prof["launches_conv0"] == 16 * prof["launches_tail"]
 
 
 def test_results_are_deterministic_and_contexts_are_independent():

@@ -19,6 +19,7 @@ for _ in range(3):
 tr = np.zeros(2048, np.int64)
 rc = _lib.load().reve_debug_trace(up._h, tr.ctypes.data, 2048)
 assert rc == 0
+print("look-ahead misses / interior rows (3 frames, CTA 0 of layer 5):", tr[2040], "/", tr[2041])
 mma = tr[:1024].reshape(256, 4)
 epi = tr[1024:].reshape(256, 4)
 t0 = mma[mma[:, 0] > 0][:, 0].min()
