@@ -184,33 +184,36 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         constexpr uint32_t kDx = 3 * NG * 8;   // one dx block of B
                 // Issue helpers (called by the elected lane only).  Part 1 = first K-step (the fresh group
         // overwrites, the others accumulate) plus three more K-steps; part 2 = the other eight.
+        // MMAs that read the same A tile back to back keep it in the tensor core's collector buffer
+        // (FILL ... LASTUSE) instead of re-reading shared memory: that makes the split MMAs of the
+        // ring-wrap rows (N=128 + N=64) cost the same tensor time as one N=192 MMA.
         auto issue_part1 = [&](uint32_t a_lo, int s0) {
             const uint64_t a0 = mk_desc(desc_hi, a_lo - 8);
             const uint32_t d = tmem_base + s0 * NG;
             if (s0 <= 5) {
-                umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
+                umma_f16_a<ACollector::FILL>(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                umma_f16_a<ACollector::LASTUSE>(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
 #pragma unroll
                 for (int dxk = 1; dxk < 4; ++dxk)
                     umma_f16(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_lo + dxk * 2), idesc3, 1u);
             } else if (s0 == 6) {
-                umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                umma_f16(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc1, 1u);
-                umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + 2 * kG), idesc1, 1u);
+                umma_f16_a<ACollector::FILL>(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                umma_f16_a<ACollector::USE>(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc1, 1u);
+                umma_f16_a<ACollector::LASTUSE>(tmem_base, a0, mk_desc(desc_hi, w_lo + 2 * kG), idesc1, 1u);
 #pragma unroll
                 for (int dxk = 1; dxk < 4; ++dxk) {
                     const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
-                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc2, 1u);
-                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + 2 * kG), idesc1, 1u);
+                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc2, 1u);
+                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + 2 * kG), idesc1, 1u);
                 }
             } else {
-                umma_f16(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                umma_f16(tmem_base, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
+                umma_f16_a<ACollector::FILL>(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
+                umma_f16_a<ACollector::LASTUSE>(tmem_base, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
 #pragma unroll
                 for (int dxk = 1; dxk < 4; ++dxk) {
                     const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
-                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc1, 1u);
-                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + kG), idesc2, 1u);
+                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc1, 1u);
+                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + kG), idesc2, 1u);
                 }
             }
         };
@@ -228,16 +231,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 for (int dxk = 4; dxk < 12; ++dxk) {
                     const int dx = dxk >> 2, k = dxk & 3;
                     const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
-                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
+                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
+                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
                 }
             } else {
 #pragma unroll
                 for (int dxk = 4; dxk < 12; ++dxk) {
                     const int dx = dxk >> 2, k = dxk & 3;
                     const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                    umma_f16(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
-                    umma_f16(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
+                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
+                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
                 }
             }
         };

@@ -179,6 +179,26 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with an A-operand collector hint: consecutive MMAs that read the same A tile keep it in the tensor
+// core's collector buffer instead of re-reading shared memory.  FILL = read A and keep it, USE = reuse and
+// keep, LASTUSE = reuse then drop (SASS: A_KEEP / A_REUSE).
+enum class ACollector { FILL, USE, LASTUSE };
+template <ACollector C>
+__device__ __forceinline__ void umma_f16_a(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    if constexpr (C == ACollector::FILL)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if constexpr (C == ACollector::USE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // all previously issued tcgen05 async ops of this thread -> one arrival on the mbarrier
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

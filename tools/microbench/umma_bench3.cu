@@ -53,6 +53,29 @@ __global__ void __launch_bounds__(320, 1) bench(int mode, int rows, Result* res)
                         const int dx = dxk >> 2, k = dxk & 3;
                         umma_f16(d, mk(desc_hi, a_lo + (dx - 1) * 8 + k * 2), mk(desc_hi, w_lo + dx * kDx + k * 2), idesc3, 1u);
                     }
+                } else if (s0 == 6 && (mode & 64)) {
+                    const uint32_t d6 = tmem_base + 6 * NG;
+                    umma_f16_a<ACollector::FILL>(d6, a0, mk(desc_hi, w_lo), idesc1, 0u);
+                    umma_f16_a<ACollector::USE>(d6 + NG, a0, mk(desc_hi, w_lo + kG), idesc1, 1u);
+                    umma_f16_a<ACollector::LASTUSE>(tmem_base, a0, mk(desc_hi, w_lo + 2 * kG), idesc1, 1u);
+#pragma unroll
+                    for (int dxk = 1; dxk < 12; ++dxk) {
+                        const int dx = dxk >> 2, k = dxk & 3;
+                        const uint64_t ad = mk(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                        umma_f16_a<ACollector::FILL>(d6, ad, mk(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
+                        umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
+                    }
+                } else if (s0 == 7 && (mode & 64)) {
+                    const uint32_t d7 = tmem_base + 7 * NG;
+                    umma_f16_a<ACollector::FILL>(d7, a0, mk(desc_hi, w_lo), idesc1, 0u);
+                    umma_f16_a<ACollector::LASTUSE>(tmem_base, a0, mk(desc_hi, w_lo + kG), idesc2, 1u);
+#pragma unroll
+                    for (int dxk = 1; dxk < 12; ++dxk) {
+                        const int dx = dxk >> 2, k = dxk & 3;
+                        const uint64_t ad = mk(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
+                        umma_f16_a<ACollector::FILL>(d7, ad, mk(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
+                        umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
+                    }
                 } else if (s0 == 6) {
                     const uint32_t d6 = tmem_base + 6 * NG;
                     umma_f16(d6, a0, mk(desc_hi, w_lo), idesc1, 0u);
@@ -103,7 +126,7 @@ int main() {
     Result* d; cudaMalloc(&d, sizeof(Result));
     for (int w = 0; w < 100; ++w) bench<<<148, 320, smem>>>(0, 2000, d);
     cudaDeviceSynchronize();
-    for (int mode : {3, 19, 51, 0, 16, 48}) {
+    for (int mode : {3, 67, 0, 64}) {
         double best = 1e30, bestns = 0;
         for (int rep = 0; rep < 3; ++rep) {
             Result h{};
@@ -112,8 +135,8 @@ int main() {
             cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
             if ((double)h.cycles / h.rows < best) { best = (double)h.cycles / h.rows; bestns = (double)h.ns / h.rows; }
         }
-        printf("mode %2d [%s%s%s%s%s%s]: %8.1f clk/row %8.1f ns/row\n", mode, mode & 1 ? "commit " : "", mode & 2 ? "trywait " : "",
-               mode & 4 ? "nowrap " : "", mode & 8 ? "12xN192 " : "", mode & 16 ? "9 spinning warps " : "", mode & 32 ? "nanosleep " : "", best, bestns);
+        printf("mode %2d [%s%s%s%s%s]: %8.1f clk/row %8.1f ns/row\n", mode, mode & 1 ? "commit " : "", mode & 2 ? "trywait " : "",
+               mode & 4 ? "nowrap " : "", mode & 8 ? "12xN192 " : "", mode & 64 ? "A-collector reuse in wrap rows " : "", best, bestns);
     }
     return 0;
 }
