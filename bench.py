@@ -35,6 +35,16 @@ BODY_FLOP_PER_PX = 2 * 9 * 64 * 64                   # one 64->64 3x3 layer
 METRIC = "frames/s animevideov3 x2 1080p->4K"
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one body launch from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01_body_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except OSError:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,7 +302,10 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"kernel": "conv3x3_umma_kernel<64,false> (64->64 3x3 + PReLU, tcgen05)",
                          "bound": "tensor", "achieved": body_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": body_tflops / peak, "traffic": None,
+                         "frac": body_tflops / peak,
+                         "traffic": (lambda t: None if not t else t["dram_bytes_per_launch"] * frames_per_launch / t["frames_per_launch"])(measured_traffic()),
+                         "traffic_unit": "bytes of DRAM read+write per launch (ncu capture profiles/r01_body_ncu_summary.txt); "
+                                         "algorithmic activation bytes per launch = 2 x 128 B x canvas pixels",
                          "peak_source": f"{psrc} bf16_tflops_sustained (kernel timed inside a long step)",
                          "avg_launch_ms": body_ms, "launches_timed": int(pr["timed_body"]),
                          "algorithmic_flop_per_launch": BODY_FLOP_PER_PX * px * frames_per_launch,
