@@ -187,7 +187,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         // MMAs that read the same A tile back to back keep it in the tensor core's collector buffer
         // (FILL ... LASTUSE) instead of re-reading shared memory: that makes the split MMAs of the
         // ring-wrap rows (N=128 + N=64) cost the same tensor time as one N=192 MMA.
-        auto issue_part1 = [&](uint32_t a_lo, int s0) {
+        auto issue_part1 = [&](uint32_t a_lo, int s0, uint32_t w_lo) {
             const uint64_t a0 = mk_desc(desc_hi, a_lo - 8);
             const uint32_t d = tmem_base + s0 * NG;
             if (s0 <= 5) {
@@ -217,7 +217,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 }
             }
         };
-        auto issue_part2 = [&](uint32_t a_lo, int s0) {
+        auto issue_part2 = [&](uint32_t a_lo, int s0, uint32_t w_lo) {
             const uint32_t d = tmem_base + s0 * NG;
             if (s0 <= 5) {
 #pragma unroll
@@ -304,7 +304,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     const int s0 = (-t0) & 7;
                     long long* const tr = (p.trace && blockIdx.x == 0 && i < 256) ? p.trace + i * 4 : nullptr;
                     if (tr && lane == 0) { tr[0] = clock64(); tr[3] = s0 << 4; }
-                    if (leader) issue_part1(a_lo, s0);
+                    // Opaque per-row copy of the weight descriptor base: keeps the compiler from hoisting 36
+                    // loop-invariant B descriptors into vector registers (two R2UR moves per MMA); the
+                    // descriptors become uniform-datapath adds on one per-row value instead.
+                    uint32_t w_row = w_lo;
+                    asm volatile("" : "+r"(w_row));
+                    if (leader) issue_part1(a_lo, s0, w_row);
                     // look ahead: barriers of the next interior row
                     bool ok = true;
                     uint32_t bar_e = 0, par_e = 0, bar_f = 0, par_f = 0;
@@ -319,7 +324,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     }
                     if (tr && lane == 0) tr[1] = clock64();
                     if (leader) {
-                        issue_part2(a_lo, s0);
+                        issue_part2(a_lo, s0, w_row);
                         umma_commit(base + kBarAEmpty + 8 * stage);
                         umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));
                     }

@@ -53,6 +53,23 @@ __global__ void __launch_bounds__(320, 1) bench(int mode, int rows, Result* res)
                         const int dx = dxk >> 2, k = dxk & 3;
                         umma_f16(d, mk(desc_hi, a_lo + (dx - 1) * 8 + k * 2), mk(desc_hi, w_lo + dx * kDx + k * 2), idesc3, 1u);
                     }
+                } else if (s0 >= 6 && (mode & 128)) {
+                    // grouped order: all K-steps of the first part, then all K-steps of the second part
+                    const int na = (s0 == 6) ? 2 : 1;                       // groups before the wrap
+                    const uint32_t da = tmem_base + s0 * NG;
+                    const uint32_t ida = na == 2 ? idesc2 : idesc1, idb = na == 2 ? idesc1 : idesc2;
+                    umma_f16(da, a0, mk(desc_hi, w_lo), idesc1, 0u);
+                    if (na == 2) umma_f16(da + NG, a0, mk(desc_hi, w_lo + kG), idesc1, 1u);
+#pragma unroll
+                    for (int dxk = 1; dxk < 12; ++dxk) {
+                        const int dx = dxk >> 2, k = dxk & 3;
+                        umma_f16(da, mk(desc_hi, a_lo + (dx - 1) * 8 + k * 2), mk(desc_hi, w_lo + dx * kDx + k * 2), ida, 1u);
+                    }
+#pragma unroll
+                    for (int dxk = 0; dxk < 12; ++dxk) {
+                        const int dx = dxk >> 2, k = dxk & 3;
+                        umma_f16(tmem_base, mk(desc_hi, a_lo + (dx - 1) * 8 + k * 2), mk(desc_hi, w_lo + dx * kDx + k * 2 + na * kG), idb, 1u);
+                    }
                 } else if (s0 == 6 && (mode & 64)) {
                     const uint32_t d6 = tmem_base + 6 * NG;
                     umma_f16_a<ACollector::FILL>(d6, a0, mk(desc_hi, w_lo), idesc1, 0u);
@@ -126,7 +143,7 @@ int main() {
     Result* d; cudaMalloc(&d, sizeof(Result));
     for (int w = 0; w < 100; ++w) bench<<<148, 320, smem>>>(0, 2000, d);
     cudaDeviceSynchronize();
-    for (int mode : {3, 67, 0, 64}) {
+    for (int mode : {3, 67, 131, 0, 64, 128, 4}) {
         double best = 1e30, bestns = 0;
         for (int rep = 0; rep < 3; ++rep) {
             Result h{};
@@ -136,7 +153,7 @@ int main() {
             if ((double)h.cycles / h.rows < best) { best = (double)h.cycles / h.rows; bestns = (double)h.ns / h.rows; }
         }
         printf("mode %2d [%s%s%s%s%s]: %8.1f clk/row %8.1f ns/row\n", mode, mode & 1 ? "commit " : "", mode & 2 ? "trywait " : "",
-               mode & 4 ? "nowrap " : "", mode & 8 ? "12xN192 " : "", mode & 64 ? "A-collector reuse in wrap rows " : "", best, bestns);
+               mode & 4 ? "nowrap " : "", mode & 8 ? "12xN192 " : "", mode & 64 ? "A-collector reuse in wrap rows " : (mode & 128 ? "grouped wrap order " : ""), best, bestns);
     }
     return 0;
 }
