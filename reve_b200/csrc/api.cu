@@ -371,7 +371,6 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     c0.row_frame = ctx->d_rowframe;
     c0.weights = ctx->d_w0;
     c0.dbg = ctx->dbg_dev;
-    c0.flags = dflags;
     for (int co = 0; co < 64; ++co) {
         c0.bias[co] = m.conv[0].b[co];
         c0.slope[co] = m.conv[0].slope[co];
@@ -385,14 +384,12 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         const int gcap = std::atoi(ge);
         if (gcap >= 1 && gcap < ctx->grid) ctx->grid = gcap;
     }
-    // Debug flags (tests / experiments): bit0 = never sweep in reverse, bit1 = no evict-first hint on
-    // activation loads, bit2 = evict-last hint on activation stores.
+    // REVE_DEBUG_FLAGS bit0 (experiments): never sweep in reverse.
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         std::memset(&p, 0, sizeof p);
         // conv0 writes the canvas top-down, so body layer 0 sweeps bottom-up, layer 1 top-down, ...
         p.reverse = (dflags & 1u) ? 0 : ((k & 1) == 0);
-        p.flags = dflags;
         p.out = (k < kNumBody) ? ctx->act[(k + 1) & 1] : nullptr;
         p.canvas_w = cw;
         p.canvas_h = ch;

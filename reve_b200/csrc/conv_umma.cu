@@ -43,6 +43,7 @@ __host__ __device__ constexpr int w_bytes(int ng) { return 3 * 3 * ng * 128; }
 __host__ __device__ constexpr int tmem_cols(int ng) { return ng * 8 <= 128 ? 128 : (ng * 8 <= 256 ? 256 : 512); }
 
 // control block offsets (from the 1024-aligned base)
+static_assert(kStages % 2 == 0, "ring slots are released in pairs");
 constexpr int kBarW = 0;
 constexpr int kBarAFull = 8;
 constexpr int kBarAEmpty = kBarAFull + 8 * kStages;
@@ -157,8 +158,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
                 const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
                 for (int y = y_lo; y <= y_hi; ++y, ++i) {
-                    const uint32_t stage = i % kStages, use = i / kStages;
-                    mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                    const uint32_t stage = i % kStages;
+                    if ((i & 1u) == 0) {  // ring slots are handed back two at a time (one commit per two rows)
+                        const uint32_t pair = (i >> 1) % (kStages / 2), usep = (i >> 1) / (kStages / 2);
+                        mbar_wait(base + kBarAEmpty + 8 * pair, (usep & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                    }
                     mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
                     tma_load_3d_hint(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage, 0,
                                      x0 - 1, rev ? CH - 1 - y : y, policy);
@@ -268,7 +272,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         umma_f16(tmem_base + ((s0 + g) & 7) * NG, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + g * kG),
                                  idesc1, (dxk == 0 && g <= fresh_hi) ? 0u : 1u);
                 }
-                umma_commit(base + kBarAEmpty + 8 * stage);  // A slot reusable once these MMAs retire
+                if (i & 1u) umma_commit(base + kBarAEmpty + 8 * ((i >> 1) % (kStages / 2)));  // rows i-1, i retired
                 if (g_hi == 2) umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));  // row y-1 complete
                 if (y == CH - 1 && yb == CH - 1)                                       // bottom edge: row y too
                     umma_commit(base + kBarAccFull + 8 * ((s0 + 1) & 7));
@@ -325,7 +329,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     if (tr && lane == 0) tr[1] = clock64();
                     if (leader) {
                         issue_part2(a_lo, s0, w_row);
-                        umma_commit(base + kBarAEmpty + 8 * stage);
+                        if (i & 1u) umma_commit(base + kBarAEmpty + 8 * ((i >> 1) % (kStages / 2)));
                         umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));
                     }
                     if (!ok) {

@@ -10,7 +10,7 @@ namespace reve {
 
 constexpr int kBoxPx = 128;    // pixels per TMA row box = UMMA M
 constexpr int kStripPx = 126;  // valid output pixels per strip row (box minus the 2 halo columns)
-constexpr int kStages = 7;     // A-row ring depth
+constexpr int kStages = 6;     // A-row ring depth (released to the producer in pairs)
 constexpr int kMaxBatch = 4;    // frames stacked on one canvas per launch (gap row between frames)
 constexpr int kConvThreads = 320;  // producer warp + MMA warp + 2 x 4 epilogue warps
 
@@ -26,7 +26,6 @@ struct ConvParams {
     const void* weights;        // pre-swizzled B operand blob of this layer (global memory)
     __half* out;                // body: output canvas [canvas_h][canvas_w][64] fp16
     int reverse;                // sweep the strip-rows bottom-up (weights blob packed accordingly)
-    uint32_t flags;             // debug/timing experiments: bit1 = no evict-first on loads, 8/32/64 = ablations
     DebugBlock* dbg;            // mapped pinned host memory, may be null
     long long* trace;           // debug timeline of CTA 0 (device memory, may be null)
     // tail only
@@ -53,7 +52,6 @@ struct Conv0Params {
     const int* row_frame;      // [canvas_h] frame of the batch (-1 = gap row)
     const void* weights;       // B operand blob (pack_conv0_weights)
     DebugBlock* dbg;
-    uint32_t flags;
     float bias[64];
     float slope[64];
 };
