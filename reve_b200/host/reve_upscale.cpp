@@ -15,9 +15,14 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -34,6 +39,7 @@ struct Options {
     std::vector<int> gpus;
     bool verbose = false;
     uint64_t seed = 1234;  // random-init fallback when the weight files are absent offline
+    int raw_w = 0, raw_h = 0;  // --raw WxH: rgb24 rawvideo frames on -i (file or "-" = stdin) -> -o (file or "-" = stdout)
 };
 
 bool ends_with(const std::string& s, const char* suf) {
@@ -47,7 +53,9 @@ bool ends_with(const std::string& s, const char* suf) {
 int usage() {
     std::fprintf(stderr,
                  "usage: reve-upscale -i in_dir -o out_dir [-s 2|3|4] [-n model-name] [-m model-dir] [-t tile]\n"
-                 "                    [-g gpu,gpu,...] [-f png] [-v]\n");
+                 "                    [-g gpu,gpu,...] [-f png] [-v]\n"
+                 "       reve-upscale --raw WxH -i in.rgb|- -o out.rgb|- [-s 2|3|4] [-m model-dir] [-t tile] [-g gpu] [-v]\n"
+                 "         (rgb24 rawvideo stream, e.g. ffmpeg -f rawvideo -pix_fmt rgb24 pipes: no PNG on the path)\n");
     return 2;
 }
 
@@ -58,11 +66,55 @@ void set_error(const std::string& e) {
     if (g_err.empty()) g_err = e;
 }
 
-// One GPU: frames idx = first, first+step, ... of `names`
+// Small fixed pool of host threads for PNG decode / encode (the upstream binary also runs 1 load and 2 save
+// threads around its GPU loop; 4K PNG encoding is the slowest step by far).
+class Pool {
+public:
+    explicit Pool(int n) {
+        for (int i = 0; i < n; ++i) threads_.emplace_back([this] { run(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(std::move(f)); ++pending_; }
+        cv_.notify_one();
+    }
+    void wait_below(size_t n) {  // block until fewer than n tasks are queued or running
+        std::unique_lock<std::mutex> l(m_);
+        done_cv_.wait(l, [&] { return pending_ < n; });
+    }
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+            { std::lock_guard<std::mutex> l(m_); --pending_; }
+            done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::deque<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+};
+
+// One GPU: frames idx = first, first+step, ... of `names`.  Decode pool -> pinned ring -> GPU -> encode pool.
 void worker(const Options& o, const reve_model* model, int device, const std::vector<std::string>& names, size_t first,
-            size_t step, int w, int h, std::atomic<bool>& failed) {
+            size_t step, int w, int h, std::atomic<bool>& failed, int host_threads) {
     reve_ctx* ctx = nullptr;
-    const int depth = 3;
+    const int depth = 8;
     if (reve_ctx_create(device, model, w, h, o.tile, o.prepad, depth, &ctx) != REVE_OK) {
         set_error(reve_last_error(nullptr));
         failed = true;
@@ -77,45 +129,137 @@ void worker(const Options& o, const reve_model* model, int device, const std::ve
             failed = true;
         }
     }
-    struct Pending { int slot; std::string src, dst; };
-    std::vector<Pending> pending;
-    auto retire = [&]() {
-        uint64_t tag = 0;
-        if (reve_wait(ctx, &tag) != REVE_OK) { set_error(reve_last_error(ctx)); failed = true; return; }
-        const Pending pd = pending.front();
-        pending.erase(pending.begin());
-        std::string err;
-        if (!reve_host::png_write(pd.dst, hout[pd.slot], w * o.scale, h * o.scale, size_t(w) * o.scale * 3, err)) {
-            set_error(err);
-            failed = true;
-            return;
+    std::vector<size_t> mine;
+    for (size_t idx = first; idx < names.size(); idx += step) mine.push_back(idx);
+
+    // decode ahead of the GPU: results keyed by position in `mine`
+    std::mutex dm;
+    std::condition_variable dcv;
+    std::map<size_t, reve_host::Image> decoded;
+    const size_t window = 16;
+    size_t next_decode = 0;
+    {
+        Pool decoders(std::max(1, host_threads / 4)), encoders(std::max(1, host_threads - host_threads / 4));
+        auto schedule_decodes = [&](size_t consumed) {
+            while (next_decode < mine.size() && next_decode < consumed + window) {
+                const size_t k = next_decode++;
+                decoders.submit([&, k] {
+                    reve_host::Image img;
+                    std::string err;
+                    if (!reve_host::png_read(o.in + "/" + names[mine[k]], img, err)) { set_error(err); failed = true; }
+                    { std::lock_guard<std::mutex> l(dm); decoded[k] = std::move(img); }
+                    dcv.notify_all();
+                });
+            }
+        };
+        struct Pending { int slot; std::string src, dst; };
+        std::deque<Pending> pending;
+        auto retire = [&]() {
+            uint64_t tag = 0;
+            if (reve_wait(ctx, &tag) != REVE_OK) { set_error(reve_last_error(ctx)); failed = true; return; }
+            Pending pd = pending.front();
+            pending.pop_front();
+            // hand a copy to the encoders so the pinned slot can be reused at once
+            auto buf = std::make_shared<std::vector<uint8_t>>(hout[pd.slot], hout[pd.slot] + out_bytes);
+            encoders.wait_below(window);
+            encoders.submit([&, buf, pd] {
+                std::string err;
+                if (!reve_host::png_write(pd.dst, buf->data(), w * o.scale, h * o.scale, size_t(w) * o.scale * 3, err)) {
+                    set_error(err);
+                    failed = true;
+                    return;
+                }
+                if (o.verbose) std::fprintf(stderr, "%s -> %s done\n", pd.src.c_str(), pd.dst.c_str());
+            });
+        };
+        schedule_decodes(0);
+        for (size_t k = 0; k < mine.size() && !failed; ++k) {
+            const int slot = static_cast<int>(k % depth);
+            if (static_cast<int>(pending.size()) == depth) retire();
+            if (failed) break;
+            reve_host::Image img;
+            {
+                std::unique_lock<std::mutex> l(dm);
+                dcv.wait(l, [&] { return decoded.count(k) != 0 || failed.load(); });
+                if (failed) break;
+                img = std::move(decoded[k]);
+                decoded.erase(k);
+            }
+            schedule_decodes(k + 1);
+            const std::string src = o.in + "/" + names[mine[k]];
+            if (img.w != w || img.h != h) { set_error(src + ": frame size differs from the first frame of the segment"); failed = true; break; }
+            std::memcpy(hin[slot], img.rgb.data(), in_bytes);
+            const std::string stem = names[mine[k]].substr(0, names[mine[k]].find_last_of('.'));
+            const std::string dst = o.out + "/" + stem + "." + o.fmt;
+            if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], size_t(w) * o.scale * 3, mine[k]) != REVE_OK) {
+                set_error(reve_last_error(ctx));
+                failed = true;
+                break;
+            }
+            pending.push_back({slot, src, dst});
         }
-        if (o.verbose) std::fprintf(stderr, "%s -> %s done\n", pd.src.c_str(), pd.dst.c_str());
-    };
-    size_t k = 0;
-    for (size_t idx = first; idx < names.size() && !failed; idx += step, ++k) {
-        const int slot = static_cast<int>(k % depth);
-        if (static_cast<int>(pending.size()) == depth) retire();
-        if (failed) break;
-        const std::string src = o.in + "/" + names[idx];
-        reve_host::Image img;
-        std::string err;
-        if (!reve_host::png_read(src, img, err)) { set_error(err); failed = true; break; }
-        if (img.w != w || img.h != h) { set_error(src + ": frame size differs from the first frame of the segment"); failed = true; break; }
-        std::memcpy(hin[slot], img.rgb.data(), in_bytes);
-        const std::string stem = names[idx].substr(0, names[idx].find_last_of('.'));
-        const std::string dst = o.out + "/" + stem + "." + o.fmt;
-        if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], size_t(w) * o.scale * 3, idx) != REVE_OK) {
-            set_error(reve_last_error(ctx));
-            failed = true;
-            break;
-        }
-        pending.push_back({slot, src, dst});
+        while (!pending.empty() && !failed) retire();
+        // Pool destructors drain the remaining decode / encode tasks
     }
-    while (!pending.empty() && !failed) retire();
     reve_sync(ctx);
     for (int i = 0; i < depth; ++i) { reve_host_free(hin[i]); reve_host_free(hout[i]); }
     reve_ctx_destroy(ctx);
+}
+
+// Raw-frame staging: a stream of packed rgb24 frames in, upscaled rgb24
+// frames out, in order, with a ring of pinned buffers so the read of frame i+k, the kernels of frame i and the
+// write of frame i-k overlap.  This is what `ffmpeg -f rawvideo -pix_fmt rgb24 pipe:1` produces and what
+// `ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH -i pipe:0 -c:v libx265 ...` consumes (replacing the PNG export /
+// image2 input of reference reve-shared/src/lib.rs:93,100-119 and reve-cli/src/main.rs:297-300).
+int run_raw(const Options& o, const reve_model* model) {
+    FILE* fin = (o.in == "-") ? stdin : std::fopen(o.in.c_str(), "rb");
+    FILE* fout = (o.out == "-") ? stdout : std::fopen(o.out.c_str(), "wb");
+    if (!fin || !fout) { std::fprintf(stderr, "error: cannot open %s\n", !fin ? o.in.c_str() : o.out.c_str()); return 1; }
+    const int w = o.raw_w, h = o.raw_h, depth = 8;
+    reve_ctx* ctx = nullptr;
+    if (reve_ctx_create(o.gpus.empty() ? 0 : o.gpus[0], model, w, h, o.tile, o.prepad, depth, &ctx) != REVE_OK) {
+        std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr));
+        return 1;
+    }
+    const size_t in_bytes = size_t(w) * h * 3, out_bytes = in_bytes * o.scale * o.scale;
+    std::vector<uint8_t*> hin(depth, nullptr), hout(depth, nullptr);
+    for (int i = 0; i < depth; ++i)
+        if (reve_host_alloc(in_bytes, reinterpret_cast<void**>(&hin[i])) != REVE_OK ||
+            reve_host_alloc(out_bytes, reinterpret_cast<void**>(&hout[i])) != REVE_OK) {
+            std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr));
+            return 1;
+        }
+    int rc = 0;
+    uint64_t submitted = 0, retired = 0;
+    auto retire = [&]() -> bool {
+        uint64_t tag = 0;
+        if (reve_wait(ctx, &tag) != REVE_OK) { std::fprintf(stderr, "error: %s\n", reve_last_error(ctx)); return false; }
+        if (std::fwrite(hout[tag % depth], 1, out_bytes, fout) != out_bytes) { std::fprintf(stderr, "error: short write\n"); return false; }
+        if (o.verbose) std::fprintf(stderr, "frame %llu -> frame %llu done\n", (unsigned long long)tag, (unsigned long long)tag);
+        ++retired;
+        return true;
+    };
+    for (;;) {
+        if (submitted - retired == static_cast<uint64_t>(depth) && !retire()) { rc = 1; break; }
+        const int slot = static_cast<int>(submitted % depth);
+        const size_t got = std::fread(hin[slot], 1, in_bytes, fin);
+        if (got == 0) break;                       // end of stream
+        if (got != in_bytes) { std::fprintf(stderr, "error: truncated frame %llu\n", (unsigned long long)submitted); rc = 1; break; }
+        if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], size_t(w) * o.scale * 3, submitted) != REVE_OK) {
+            std::fprintf(stderr, "error: %s\n", reve_last_error(ctx));
+            rc = 1;
+            break;
+        }
+        ++submitted;
+    }
+    while (rc == 0 && retired < submitted) if (!retire()) rc = 1;
+    std::fflush(fout);
+    reve_sync(ctx);
+    for (int i = 0; i < depth; ++i) { reve_host_free(hin[i]); reve_host_free(hout[i]); }
+    reve_ctx_destroy(ctx);
+    if (fin != stdin) std::fclose(fin);
+    if (fout != stdout) std::fclose(fout);
+    return rc;
 }
 
 }  // namespace
@@ -137,6 +281,10 @@ int main(int argc, char** argv) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : nullptr; };
         if (a == "-v") o.verbose = true;
+        else if (a == "--raw") {
+            const char* v = (i + 1 < argc) ? argv[++i] : nullptr;
+            if (!v || std::sscanf(v, "%dx%d", &o.raw_w, &o.raw_h) != 2 || o.raw_w < 1 || o.raw_h < 1) return usage();
+        }
         else if (a == "-x") { std::fprintf(stderr, "error: TTA (-x) is not supported\n"); return 2; }
         else if (a == "-i" || a == "-o" || a == "-s" || a == "-n" || a == "-m" || a == "-t" || a == "-g" || a == "-f" || a == "-j") {
             const char* v = next();
@@ -155,13 +303,16 @@ int main(int argc, char** argv) {
     if (o.tile < 0) o.tile = 200;
 
     std::vector<std::string> names;
-    if (DIR* d = opendir(o.in.c_str())) {
+    if (o.raw_w > 0) {
+        names.push_back("raw");   // stream mode: no directory
+    } else if (DIR* d = opendir(o.in.c_str())) {
         while (dirent* e = readdir(d)) if (ends_with(e->d_name, ".png")) names.push_back(e->d_name);
         closedir(d);
     } else { std::fprintf(stderr, "error: cannot open input directory %s\n", o.in.c_str()); return 1; }
     std::sort(names.begin(), names.end());
-    for (size_t pos = 1; pos <= o.out.size(); ++pos)   // mkdir -p (the reference creates only the leaf, lib.rs:130-132)
-        if (pos == o.out.size() || o.out[pos] == '/') mkdir(o.out.substr(0, pos).c_str(), 0777);
+    if (o.raw_w == 0)
+        for (size_t pos = 1; pos <= o.out.size(); ++pos)   // mkdir -p (the reference creates only the leaf, lib.rs:130-132)
+            if (pos == o.out.size() || o.out[pos] == '/') mkdir(o.out.substr(0, pos).c_str(), 0777);
     if (names.empty()) return 0;
 
     // upstream appends "-x<scale>" only to the bare name; reve passes "...-x2" whatever -s is (lib.rs:141)
@@ -180,6 +331,11 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "warning: %s.param/.bin not found, using the seeded random init of the architecture\n", stem.c_str());
         if (reve_model_random(o.scale, o.seed, &model) != REVE_OK) { std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr)); return 1; }
     }
+    if (o.raw_w > 0) {
+        const int rc = run_raw(o, model);
+        reve_model_free(model);
+        return rc;
+    }
     reve_host::Image first;
     std::string err;
     if (!reve_host::png_read(o.in + "/" + names[0], first, err)) { std::fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
@@ -187,8 +343,10 @@ int main(int argc, char** argv) {
 
     std::atomic<bool> failed{false};
     std::vector<std::thread> threads;
+    const int host_threads = std::max(2, static_cast<int>(std::thread::hardware_concurrency()) / static_cast<int>(o.gpus.size()) - 1);
     for (size_t g = 0; g < o.gpus.size(); ++g)
-        threads.emplace_back(worker, std::cref(o), model, o.gpus[g], std::cref(names), g, o.gpus.size(), first.w, first.h, std::ref(failed));
+        threads.emplace_back(worker, std::cref(o), model, o.gpus[g], std::cref(names), g, o.gpus.size(), first.w, first.h,
+                             std::ref(failed), host_threads);
     for (auto& t : threads) t.join();
     reve_model_free(model);
     if (failed) { std::fprintf(stderr, "error: %s\n", g_err.c_str()); return 1; }

@@ -64,3 +64,29 @@ def test_cli_is_a_drop_in_for_the_spawned_upscaler(exe, tmp_path):
         got = cv2.imread(str(outdir / f"frame{i + 1:08d}.png"), cv2.IMREAD_COLOR)[:, :, ::-1]
         par = srvgg.parity(got, srvgg.upscale(f, wts, tile=200, prepad=10))
         assert par["within1"] >= 0.999 and par["psnr"] >= 50, par
+
+
+@pytest.mark.gpu
+def test_raw_rgb24_stream_mode(exe, tmp_path):
+    """Raw-frame staging: rgb24 rawvideo in -> rgb24 out, frames in order."""
+    w, h, n, s = 160, 90, 11, 2
+    frames = [srvgg.synthetic_frame(w, h, 50 + i, "random" if i % 2 else "edges") for i in range(n)]
+    src, dst = tmp_path / "in.rgb", tmp_path / "out.rgb"
+    src.write_bytes(b"".join(f.tobytes() for f in frames))
+    r = subprocess.run([exe, "--raw", f"{w}x{h}", "-i", str(src), "-o", str(dst), "-s", str(s), "-v",
+                        "-m", str(tmp_path / "no_models")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert sum("done" in l for l in r.stderr.splitlines()) == n
+    out = np.frombuffer(dst.read_bytes(), np.uint8).reshape(n, h * s, w * s, 3)
+    wts = srvgg.make_weights(s, 1234)
+    for i in (0, 3, 10):
+        par = srvgg.parity(out[i], srvgg.upscale(frames[i], wts, tile=200, prepad=10))
+        assert par["within1"] >= 0.999 and par["psnr"] >= 50, (i, par)
+    # stdin / stdout pipes
+    p = subprocess.run([exe, "--raw", f"{w}x{h}", "-i", "-", "-o", "-", "-s", str(s), "-m", str(tmp_path / "no_models")],
+                       input=src.read_bytes(), capture_output=True)
+    assert p.returncode == 0 and p.stdout == dst.read_bytes()
+    # a truncated stream is an error, not silently dropped
+    (tmp_path / "bad.rgb").write_bytes(src.read_bytes()[:-5])
+    assert subprocess.call([exe, "--raw", f"{w}x{h}", "-i", str(tmp_path / "bad.rgb"), "-o", str(tmp_path / "o.rgb"),
+                            "-m", str(tmp_path / "no_models")], stderr=subprocess.DEVNULL) == 1
