@@ -9,8 +9,8 @@
 // 0..255 as fp16, canonical K-major no-swizzle core-matrix layout), one warp issues two K=16 MMAs
 // per tile into a ring of TMEM accumulators, and two epilogue groups apply (acc/255 + bias), PReLU,
 // gap zeroing and write the row-major fp16 tile with one TMA store.
-// Warp roles (544 threads): warps 0-7 = two producer groups (alternate tiles), warp 8 = TMEM
-// allocator + MMA issuer, warps 9-16 = two epilogue groups (alternate tiles).  The src_x / src_y
+// Warp roles (672 threads): warps 0-11 = three producer groups (tiles round-robin), warp 12 = TMEM
+// allocator + MMA issuer, warps 13-20 = two epilogue groups (alternate tiles).  The src_x / src_y
 // geometry tables are cached in shared memory so the gather needs one global round trip per tile.
 #include "kernels.h"
 
@@ -22,12 +22,13 @@ namespace reve {
 
 namespace {
 
-constexpr int kProducerWarps = 8;            // two groups of 4: alternate tiles
+constexpr int kProducerGroups = 3;           // groups of 4 warps take tiles round-robin
+constexpr int kProducerWarps = 4 * kProducerGroups;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kFirstEpiWarp = kMmaWarp + 1;  // 8 epilogue warps; TMEM lane quarter = warp % 4
 constexpr int kThreads = (kFirstEpiWarp + 8) * 32;
 constexpr int kMaxTableInts = 12288;         // src_x / src_y cached in shared memory when they fit (48 KB)
-constexpr int kStagesA = 4;
+constexpr int kStagesA = 6;             // multiple of kProducerGroups: a group always fills the same stages
 constexpr int kTileA = 128 * 64;       // 8 KB: 128 px x 32 k x fp16
 constexpr int kAccBufs = 4;            // TMEM accumulator ring: 4 x 64 columns
 constexpr int kWBytes0 = 64 * 64;      // 4 KB: 64 co x 32 k x fp16
@@ -132,7 +133,7 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         const int m = (warp & 3) * 32 + lane;
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-            if ((j & 1) != static_cast<uint32_t>(pg)) continue;
+            if ((j % kProducerGroups) != static_cast<uint32_t>(pg)) continue;
             const uint32_t stage = j % kStagesA, use = j / kStagesA;
             const long long px = static_cast<long long>(tile) * 128 + m;
             uint32_t w[16];

@@ -425,10 +425,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
                         const float xin[3] = {static_cast<float>(sp[0]), static_cast<float>(sp[1]),
                                               static_cast<float>(sp[2])};
+                        // S*3 consecutive bytes per output row: packed into 16-/32-bit stores when aligned
+                        const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
 #pragma unroll
                         for (int i = 0; i < S; ++i) {
                             uint8_t* dp = p.dst[fr] + static_cast<long long>(oy * S + i) * p.dst_stride +
                                           static_cast<long long>(ox) * (S * 3);
+                            uint32_t b[S * 3];
 #pragma unroll
                             for (int j = 0; j < S; ++j) {
 #pragma unroll
@@ -439,8 +442,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                                     // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5))
                                     float o = floorf(fmaf(v, 255.f, xin[c] + 0.5f));
                                     o = fminf(fmaxf(o, 0.f), 255.f);
-                                    dp[j * 3 + c] = static_cast<uint8_t>(o);
+                                    b[j * 3 + c] = static_cast<uint32_t>(o);
                                 }
+                            }
+                            if (wide && S == 2) {
+                                uint16_t* d16 = reinterpret_cast<uint16_t*>(dp);   // 6*ox: 2-byte aligned
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) d16[k] = static_cast<uint16_t>(b[2 * k] | (b[2 * k + 1] << 8));
+                            } else if (wide && S == 4) {
+                                uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);   // 12*ox: 4-byte aligned
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    d32[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < S * 3; ++k) dp[k] = static_cast<uint8_t>(b[k]);
                             }
                         }
                     }
