@@ -114,11 +114,7 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
     const int* const tx = tab_smem ? tab : p.src_x;
     const int* const ty = tab_smem ? tab + CW : p.src_y;
     const int* const tf = tab_smem ? tab + CW + CHh : p.row_frame;
-    if (warp == kFirstEpiWarp && lane == 0) {
-        prefetch_tmap(&out_map);
-        mbar_arrive_expect_tx(base + kBarW, kWBytes0);
-        bulk_load_1d(base + kOffW, p.weights, kWBytes0, base + kBarW);
-    }
+    if (warp == kFirstEpiWarp && lane == 0) prefetch_tmap(&out_map);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -179,6 +175,11 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {   // weights: one bulk copy (after the barrier-init __syncthreads above)
+            mbar_arrive_expect_tx(base + kBarW, kWBytes0);
+            bulk_load_1d(base + kOffW, p.weights, kWBytes0, base + kBarW);
+        }
+        __syncwarp();
         mbar_wait(base + kBarW, 0, dbg, TAG0_W);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_f16(128, 64);
