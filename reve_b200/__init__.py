@@ -4,9 +4,9 @@ The product is ``libreve_cuda.so`` (hand-written CUDA behind the C ABI in ``incl
 this package is the thin Python host mirror used by the tests and ``bench.py``.  It never falls
 back to a CPU path: if the shared library or an sm_100 device is missing, it raises.
 """
-from .segments import last_segment_size, segment_table, shard_segments
+from .segments import VideoState, last_segment_size, segment_table, shard_segments
 from .upscaler import (Model, Upscaler, ReveError, load_library, library_path, geometry,
                        upscale_segment)
 
 __all__ = ["Model", "Upscaler", "ReveError", "load_library", "library_path", "geometry",
-           "upscale_segment", "segment_table", "last_segment_size", "shard_segments"]
+           "upscale_segment", "segment_table", "last_segment_size", "shard_segments", "VideoState"]

@@ -73,3 +73,38 @@ def test_two_rank_gloo_sharding_and_timing_reduction():
         assert mx[0] == 11.0 and mx[1] == 4.0                 # MAX over ranks (time, count)
         assert sorted(sum(gathered, [])) == list(range(7))    # the two shards partition the queue
         assert gathered[0] == [0, 2, 4, 6] and gathered[1] == [1, 3, 5]
+
+
+def test_video_state_is_compatible_with_the_reference_json_and_behaves_as_a_set():
+    # a video.temp as reve-cli writes it (serde field order of reve-shared/src/lib.rs:16-25)
+    ref_json = ('{"path":"in.mkv","output_path":"out.mkv","segments":[{"index":2,"size":1000},{"index":3,"size":1000},'
+                '{"index":4,"size":439}],"frame_rate":23.976,"frame_count":4440,"segment_size":1000,'
+                '"segment_count":5,"upscale_ratio":2}')
+    v = reve_b200.VideoState.from_json(ref_json)
+    assert v.remaining() == [2, 3, 4] and v.segment_count == 5 and v.upscale_ratio == 2
+    import json
+    assert json.loads(v.to_json()) == json.loads(ref_json)          # round trip, same schema
+    assert v.assignment(2) == [[2, 4], [3]]
+    v.mark_done(3)                                                   # out-of-order completion
+    assert v.remaining() == [2, 4]
+    with pytest.raises(KeyError):
+        v.mark_done(3)
+    # resume: part files of still-pending segments are stale (the reference deletes video_parts\{first}.mp4)
+    assert v.resume_fixup(parts_present=[0, 1, 2, 3]) == [2]
+    n = reve_b200.VideoState.new("a.mp4", "b.mp4", 1440, 23.976, 1000, 3)
+    assert n.segments == [(0, 1000), (1, 439)] and n.segment_count == 2
+
+
+def test_bench_reference_arm_emits_the_contract_json():
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-budget", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "dtype",
+              "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
