@@ -387,7 +387,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     // REVE_DEBUG_FLAGS bit0 (experiments): never sweep in reverse.
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
-        std::memset(&p, 0, sizeof p);
+        p = ConvParams{};
         // conv0 writes the canvas top-down, so body layer 0 sweeps bottom-up, layer 1 top-down, ...
         p.reverse = (dflags & 1u) ? 0 : ((k & 1) == 0);
         p.out = (k < kNumBody) ? ctx->act[(k + 1) & 1] : nullptr;
@@ -410,6 +410,8 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             p.bias[c] = L.b[c];
             p.slope[c] = L.slope.empty() ? 0.f : L.slope[c];
         }
+        if (!L.slope.empty())
+            for (int c = 0; c < 64; c += 2) p.slope2[c >> 1] = __floats2half2_rn(L.slope[c], L.slope[c + 1]);
     }
 
     if (std::getenv("REVE_DEBUG_TRACE")) {

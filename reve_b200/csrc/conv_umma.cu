@@ -77,10 +77,6 @@ struct SegIter {
     }
 };
 
-__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
 __device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t lo) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
@@ -396,19 +392,27 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     if (m >= 1 && m <= kStripPx) {
                         const int row = m - 1;
                         const uint32_t rbase = stg + row * 128;
+                        if (keep) {
 #pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) {
-                            uint32_t pk[4];
+                            for (int c8 = 0; c8 < 8; ++c8) {
+                                uint32_t pk[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int ch = c8 * 8 + j * 2;
-                                float v0 = __uint_as_float(acc[ch]) + p.bias[ch];
-                                float v1 = __uint_as_float(acc[ch + 1]) + p.bias[ch + 1];
-                                v0 = fmaxf(v0, 0.f) + p.slope[ch] * fminf(v0, 0.f);
-                                v1 = fmaxf(v1, 0.f) + p.slope[ch + 1] * fminf(v1, 0.f);
-                                pk[j] = keep ? pack_half2(v0, v1) : 0u;
+                                for (int j = 0; j < 4; ++j) {
+                                    const int ch = c8 * 8 + j * 2;
+                                    // bias in fp32, then PReLU on the packed fp16 pair: max(v,0) + a*min(v,0).
+                                    // Positive values are bit-identical to the fp32 formulation; negative ones
+                                    // round twice (<= 1 ulp of fp16 instead of 0.5).
+                                    const __half2 v = __floats2half2_rn(__uint_as_float(acc[ch]) + p.bias[ch],
+                                                                        __uint_as_float(acc[ch + 1]) + p.bias[ch + 1]);
+                                    const __half2 z = __float2half2_rn(0.f);
+                                    const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                                    pk[j] = *reinterpret_cast<const uint32_t*>(&r);
+                                }
+                                st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                             }
-                            st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                        } else {   // gap pixel (between tiles / frames): must read as zero in the next layer
+#pragma unroll
+                            for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + (c8 << 4), 0u, 0u, 0u, 0u);
                         }
                     }
                     fence_proxy_async_smem();

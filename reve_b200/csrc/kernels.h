@@ -39,6 +39,7 @@ struct ConvParams {
     const int* out_y;           // [canvas_h]
     float bias[64];
     float slope[64];
+    __half2 slope2[32];         // body: PReLU slopes as packed fp16 pairs (epilogue half2 math)
 };
 
 // First convolution (3 -> 64) + PReLU on tensor cores (K = 27 padded to 32), fused with the u8 -> fp16
