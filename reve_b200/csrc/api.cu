@@ -65,6 +65,7 @@ struct reve_ctx {
     ConvParams body[kNumBody];
     ConvParams tail;
     int grid = 0;
+    bool pair = false;    // body layers run as CTA pairs (tcgen05 cta_group::2)
     DebugBlock* dbg_host = nullptr;
     DebugBlock* dbg_dev = nullptr;
     long long* d_trace = nullptr;  // REVE_DEBUG_TRACE: timeline of CTA 0 of body layer 5
@@ -154,7 +155,7 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
         ConvParams b = ctx->body[k];
         b.canvas_h = ch;
         b.total_rows = static_cast<int>(total);
-        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], b));
+        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->pair && grid >= 2, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], b));
         ctx->prof.launches_body++;
         ctx->prof.body_frames += n;
         prof_mark(ctx, 1);
@@ -384,12 +385,14 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         const int gcap = std::atoi(ge);
         if (gcap >= 1 && gcap < ctx->grid) ctx->grid = gcap;
     }
-    // REVE_DEBUG_FLAGS bit0 (experiments): never sweep in reverse.
+    // REVE_DEBUG_FLAGS bit0 (experiments): never sweep in reverse; bit1: CTA pairs; bit2: swap the pair's B halves.
+    ctx->pair = (dflags & 2u) != 0;
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         p = ConvParams{};
         // conv0 writes the canvas top-down, so body layer 0 sweeps bottom-up, layer 1 top-down, ...
         p.reverse = (dflags & 1u) ? 0 : ((k & 1) == 0);
+        p.flags = (dflags & 4u) ? 1u : 0u;
         p.out = (k < kNumBody) ? ctx->act[(k + 1) & 1] : nullptr;
         p.canvas_w = cw;
         p.canvas_h = ch;

@@ -10,20 +10,29 @@
 //     pixel) lands in a 16 KB ring slot; the three horizontal taps are the same slot read through
 //     descriptors shifted by -1/0/+1 pixel (128 B).  Output columns 0 and 127 of the M-tile are
 //     halo garbage and are never stored.
-//   * The three vertical taps are stacked along N: for input row y the B operand is
-//     [W(ky=0) | W(ky=1) | W(ky=2)] (N = 3*NG), so one read of the A tile feeds output rows
-//     y+1, y, y-1, whose accumulators sit in adjacent NG-column slots of an 8-slot TMEM ring
-//     (slot(t) = (-t) mod 8, so the three slots are ascending and contiguous except at the
-//     wrap, where the MMA is split).  Every input row is fetched from L2/HBM exactly once per
-//     strip and A is read from shared memory 12 times per row instead of 36.
-//   * A CTA owns a contiguous range of strip-rows (grid = #SMs, persistent), possibly spanning two
-//     strips; segments restart the 3-row window with their own halo rows.
-//   * Alternate layers sweep their ranges in opposite directions (`reverse`): the rows a CTA wrote
-//     last in layer l are the rows it reads first in layer l+1, while they are still in L2.
+//   * The three vertical taps are stacked along N: the B operand of input row y is the three
+//     weight groups W(ky=0..2) (N = 3*NG), so one read of the A tile feeds output rows y+1, y, y-1.
+//   * Rotating accumulator bank: a stream of consecutive rows owns 3 TMEM slots of NG columns; the
+//     accumulator of the row whose centre tap is step e lives in slot e mod 3, so every step
+//     writes all three slots with ONE N = 3*NG MMA per K-step whose B operand is a cyclic rotation
+//     of the three groups (the blob holds [W2|W1|W0|W2|W1], a rotation is a start offset).  No
+//     MMA is ever split and none overwrites: the epilogue hands a slot back zeroed (tcgen05.st).
+//   * The slot completed by step k is needed again, empty, by step k+1 of the same stream.  Each
+//     CTA therefore interleaves TWO independent streams (two halves of its range of strip-rows,
+//     one accumulator bank and one epilogue group each): while one stream's slot is drained the
+//     tensor pipe runs the other stream's step.
+//   * A stream walks its range segment by segment (a segment = consecutive rows of one strip);
+//     a segment of n rows is n+2 steps (one halo row either side; rows outside the canvas are
+//     TMA zero fill).  The "event" whose centre is a halo step collects garbage and is only zeroed.
+//   * CTA pairs (body kernel): two CTAs of a cluster run their streams in lock-step through
+//     tcgen05.mma.cta_group::2 (M = 256: each CTA's own A tile, half of B's rows from each CTA's
+//     shared memory), which halves the B-operand shared-memory reads per SM; the even CTA issues.
+//   * Alternate layers sweep in opposite directions (`reverse`): the rows a CTA wrote last in
+//     layer l are the rows it reads first in layer l+1, while they may still be in L2.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warp-
-// uniform code, one elected lane issues), warps 2..9 = two epilogue groups that take alternate
-// output rows (TMEM -> registers -> bias/PReLU -> fp16 -> swizzled smem -> TMA store, or for the tail:
-// bias -> PixelShuffle + residual -> u8 -> global).
+// uniform code, one elected lane issues), warps 2..5 / 6..9 = epilogue group of stream 0 / 1
+// (TMEM -> registers -> zero the slot -> bias/PReLU -> fp16 -> swizzled smem -> TMA store, or for
+// the tail: bias -> PixelShuffle + residual -> u8 -> global).
 #include "kernels.h"
 
 #include <algorithm>
@@ -38,42 +47,96 @@ namespace {
 constexpr int kRowBytes = kBoxPx * 128;  // 16 KB: 128 px * 64 ch * fp16
 constexpr int kCtrlBytes = 2048;
 constexpr int kGuard = 1024;
+constexpr int kMaxStages = 8;
 
-__host__ __device__ constexpr int w_bytes(int ng) { return 3 * 3 * ng * 128; }
-__host__ __device__ constexpr int tmem_cols(int ng) { return ng * 8 <= 128 ? 128 : (ng * 8 <= 256 ? 256 : 512); }
+__host__ __device__ constexpr int rows_per_dx(int ng, bool pair) { return pair ? 7 * ng / 2 : 5 * ng; }
+__host__ __device__ constexpr int w_smem_bytes(int ng, bool pair) { return 3 * rows_per_dx(ng, pair) * 128; }
+__host__ __device__ constexpr int tmem_cols(int ng) { return ng * 6 <= 128 ? 128 : (ng * 6 <= 256 ? 256 : 512); }
+// A-row ring depth: what fits next to the weights (body, one CTA: 120 KB of weights leave room for 4 rows)
+__host__ __device__ constexpr int ring_stages(int ng, bool tail, bool pair) { return (ng == 64 && !tail && !pair) ? 4 : 6; }
 
 // control block offsets (from the 1024-aligned base)
-static_assert(kStages % 2 == 0, "ring slots are released in pairs");
 constexpr int kBarW = 0;
-constexpr int kBarAFull = 8;
-constexpr int kBarAEmpty = kBarAFull + 8 * kStages;
-constexpr int kBarAccFull = kBarAEmpty + 8 * kStages;
-constexpr int kBarAccEmpty = kBarAccFull + 8 * 8;
+constexpr int kBarWPeer = 8;
+constexpr int kBarAFull = 16;
+constexpr int kBarAEmpty = kBarAFull + 8 * kMaxStages;
+constexpr int kBarAccFull = kBarAEmpty + 8 * kMaxStages;   // [stream][slot]
+constexpr int kBarAccEmpty = kBarAccFull + 8 * 6;           // [stream][slot]
 constexpr int kTmemPtr = 512;
 constexpr int kOffBias = 1024;   // 64 floats
 constexpr int kOffSlope = 1280;  // 64 floats
+static_assert(kBarAccEmpty + 8 * 6 <= kTmemPtr, "control block overflow");
 
-enum : uint32_t { TAG_W = 1, TAG_A_EMPTY = 2, TAG_A_FULL = 3, TAG_ACC_EMPTY = 4, TAG_ACC_FULL = 5 };
+enum : uint32_t { TAG_W = 1, TAG_A_EMPTY = 2, TAG_A_FULL = 3, TAG_ACC_EMPTY = 4, TAG_ACC_FULL = 5, TAG_W_PEER = 6 };
 
-// Range of (virtual) strip-rows of this CTA, cut into per-strip segments.  In reverse mode the
-// virtual index runs backwards over the physical one (strip' = n_strips-1-strip, y' = CH-1-y) and
-// the CTA takes the mirrored block, i.e. the same physical region as in forward mode.
-struct SegIter {
-    long long lo, hi;
+// Range of (virtual) strip-rows of one stream.  A worker (CTA, or CTA pair) owns a contiguous block of
+// total_rows / n_workers strip-rows, cut evenly into its 2 (4) streams.  In reverse mode the virtual
+// index runs backwards over the physical one (strip' = n_strips-1-strip, y' = CH-1-y) and the worker
+// takes the mirrored block, i.e. the same physical region as in forward mode.
+template <bool PAIR>
+__device__ __forceinline__ void stream_range(const ConvParams& p, uint32_t rank, int s, long long& lo, long long& hi) {
+    const unsigned n_workers = PAIR ? gridDim.x / 2 : gridDim.x;
+    const unsigned w = PAIR ? blockIdx.x / 2 : blockIdx.x;
+    const unsigned b = p.reverse ? (n_workers - 1 - w) : w;
+    const long long wlo = static_cast<long long>(b) * p.total_rows / n_workers;
+    const long long whi = static_cast<long long>(b + 1) * p.total_rows / n_workers;
+    const int n_streams = PAIR ? 4 : 2;
+    const int q = PAIR ? static_cast<int>(rank) * 2 + s : s;
+    lo = wlo + (whi - wlo) * q / n_streams;
+    hi = wlo + (whi - wlo) * (q + 1) / n_streams;
+}
+// steps of a stream: every segment (rows of one strip) costs its rows plus two halo rows
+__device__ __forceinline__ int stream_steps(long long lo, long long hi, int ch) {
+    if (hi <= lo) return 0;
+    const int n_seg = static_cast<int>((hi - 1) / ch - lo / ch) + 1;
+    return static_cast<int>(hi - lo) + 2 * n_seg;
+}
+
+// Walks the steps of a stream: (strip, virtual row y, interior?).  Past the end it yields padding steps
+// (row -1 = outside the canvas, never interior) so that the two CTAs of a pair stay in lock-step.
+struct Cursor {
+    long long pos, hi;
     int ch;
-    __device__ SegIter(const ConvParams& p) : ch(p.canvas_h) {
-        const unsigned b = p.reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-        lo = static_cast<long long>(b) * p.total_rows / gridDim.x;
-        hi = static_cast<long long>(b + 1) * p.total_rows / gridDim.x;
+    int strip = 0, ya = 0, yb = -2, y = 0;
+    __device__ Cursor(long long lo_, long long hi_, int ch_) : pos(lo_), hi(hi_), ch(ch_) {}
+    __device__ bool next(int& strip_o, int& y_o, bool& new_segment) {
+        new_segment = false;
+        if (y > yb + 1) {
+            if (pos >= hi) {
+                strip_o = strip;
+                y_o = -1;
+                return false;
+            }
+            strip = static_cast<int>(pos / ch);
+            ya = static_cast<int>(pos % ch);
+            const long long n = min(static_cast<long long>(ch - ya), hi - pos);
+            yb = ya + static_cast<int>(n) - 1;
+            pos += n;
+            y = ya - 1;
+            new_segment = true;
+        }
+        strip_o = strip;
+        y_o = y;
+        const bool interior = (y >= ya) && (y <= yb);
+        ++y;
+        return interior;
     }
-    __device__ bool next(int& strip, int& ya, int& yb) {
-        if (lo >= hi) return false;
-        strip = static_cast<int>(lo / ch);
-        ya = static_cast<int>(lo % ch);
-        const long long n = min(static_cast<long long>(ch - ya), hi - lo);
-        yb = ya + static_cast<int>(n) - 1;
-        lo += n;
-        return true;
+};
+
+// Interleaved order of the steps of the two streams: k = 1, 2, ...; stream 0 then stream 1 (each while it
+// still has steps).  Producer, MMA issuer and (implicitly) the epilogue groups all follow this order.
+struct Sequencer {
+    int u0, u1, k = 1, s = -1;
+    __device__ Sequencer(int u0_, int u1_) : u0(u0_), u1(u1_) {}
+    __device__ bool next() {
+        for (;;) {
+            if (++s == 2) {
+                s = 0;
+                ++k;
+            }
+            if (k > u0 && k > u1) return false;
+            if (k <= (s == 0 ? u0 : u1)) return true;
+        }
     }
 };
 
@@ -88,15 +151,20 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int NG, bool TAIL>
+template <int NG, bool TAIL, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                     const __grid_constant__ ConvParams p) {
-    constexpr int kWBytes = w_bytes(NG);
+    constexpr int kStages = ring_stages(NG, TAIL, PAIR);
+    constexpr int kRowsDx = rows_per_dx(NG, PAIR);
+    constexpr int kWBytes = w_smem_bytes(NG, PAIR);
+    constexpr int kBank = 3 * NG;               // TMEM columns of one stream's accumulator bank
     constexpr int kTmemCols = tmem_cols(NG);
     constexpr int kOffW = kCtrlBytes;
     constexpr int kOffRing = kOffW + kWBytes + kGuard;
     constexpr int kOffStage = kOffRing + kStages * kRowBytes + kGuard;  // body: 2 x 16 KB output staging (one per group)
+    static_assert(kWBytes % 1024 == 0, "the A ring must stay 1024-byte aligned");
+    static_assert(kStages <= kMaxStages, "ring too deep for the control block");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -106,30 +174,36 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     DebugBlock* const dbg = p.dbg;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = (rank == 0);
 
     if (threadIdx.x == 0) {
         mbar_init(base + kBarW, 1);
+        mbar_init(base + kBarWPeer, 1);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(base + kBarAFull + 8 * s, 1);
             mbar_init(base + kBarAEmpty + 8 * s, 1);
         }
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < 6; ++s) {
             mbar_init(base + kBarAccFull + 8 * s, 1);
-            mbar_init(base + kBarAccEmpty + 8 * s, 4);  // one arrive per warp of the draining group
+            mbar_init(base + kBarAccEmpty + 8 * s, PAIR ? 8 : 4);  // one arrive per warp of the draining group(s)
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(base + kTmemPtr, kTmemCols);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(base + kTmemPtr, kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(base + kTmemPtr, kTmemCols);
+            tmem_relinquish();
+        }
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&in_map);
         if (!TAIL) prefetch_tmap(&out_map);
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
-        // bias / PReLU slopes: shared-memory copies, read back as broadcast LDS.128 in the epilogue
-        // (constant-bank operands turn into long-latency LDCU loads on sm_100)
         reinterpret_cast<float*>(base_ptr + kOffBias)[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
         reinterpret_cast<float*>(base_ptr + kOffSlope)[threadIdx.x - 64] = p.slope[threadIdx.x - 64];
     }
@@ -141,327 +215,304 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     const int CH = p.canvas_h;
     const bool rev = p.reverse != 0;
 
+    // steps per stream; in a pair both CTAs run the larger count (the shorter stream pads)
+    int U[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        long long lo, hi;
+        stream_range<PAIR>(p, rank, s, lo, hi);
+        U[s] = stream_steps(lo, hi, CH);
+        if constexpr (PAIR) {
+            stream_range<PAIR>(p, rank ^ 1u, s, lo, hi);
+            U[s] = max(U[s], stream_steps(lo, hi, CH));
+        }
+    }
+
+    if (warp >= 2) {
+        // every accumulator slot starts out zero: this group's bank, this warp's 32 lanes
+        const int grp = (warp - 2) >> 2;
+        const uint32_t t = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + grp * kBank;
+#pragma unroll
+        for (int c = 0; c < kBank / 16; ++c) tmem_st16_fill(t + c * 16, 0u);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(base + kBarW, kWBytes);
-            bulk_load_1d(base + kOffW, p.weights, kWBytes, base + kBarW);
+            if constexpr (PAIR) {
+                // this CTA's half of every rotation: rows [rank * 1.5 NG, +3.5 NG) of each dx block of the blob
+                const uint32_t r = rank ^ (p.flags & 1u);
+                mbar_arrive_expect_tx(base + kBarW, kWBytes);
+                for (int dx = 0; dx < 3; ++dx)
+                    bulk_load_1d(base + kOffW + dx * kRowsDx * 128,
+                                 static_cast<const uint8_t*>(p.weights) + (dx * 5 * NG + r * (3 * NG / 2)) * 128,
+                                 kRowsDx * 128, base + kBarW);
+            } else {
+                mbar_arrive_expect_tx(base + kBarW, kWBytes);
+                bulk_load_1d(base + kOffW, p.weights, kWBytes, base + kBarW);
+            }
             const uint64_t policy = kPolicyEvictFirst;  // activations are read once per layer
-            SegIter it(p);
-            int strip, ya, yb;
+            long long lo0, hi0, lo1, hi1;
+            stream_range<PAIR>(p, rank, 0, lo0, hi0);
+            stream_range<PAIR>(p, rank, 1, lo1, hi1);
+            Cursor cur0(lo0, hi0, CH), cur1(lo1, hi1, CH);
+            Sequencer seq(U[0], U[1]);
+            const uint32_t full_base = PAIR ? mapa_u32(base + kBarAFull, 0) : (base + kBarAFull);   // the even CTA's barriers
             uint32_t i = 0;
-            while (it.next(strip, ya, yb)) {
+            while (seq.next()) {
+                int strip, y;
+                bool newseg;
+                if (seq.s == 0) cur0.next(strip, y, newseg); else cur1.next(strip, y, newseg);
                 const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
-                const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
-                for (int y = y_lo; y <= y_hi; ++y, ++i) {
-                    const uint32_t stage = i % kStages;
-                    if ((i & 1u) == 0) {  // ring slots are handed back two at a time (one commit per two rows)
-                        const uint32_t pair = (i >> 1) % (kStages / 2), usep = (i >> 1) / (kStages / 2);
-                        mbar_wait(base + kBarAEmpty + 8 * pair, (usep & 1) ^ 1, dbg, TAG_A_EMPTY, i);
-                    }
+                const uint32_t stage = i % kStages, use = i / kStages;
+                mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                if constexpr (PAIR) {
+                    if (leader) mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, 2 * kRowBytes);
+                    tma_load_3d_hint_pair(base + kOffRing + stage * kRowBytes, &in_map, full_base + 8 * stage, 0,
+                                          x0 - 1, rev ? CH - 1 - y : y, policy);
+                } else {
                     mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
                     tma_load_3d_hint(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage, 0,
                                      x0 - 1, rev ? CH - 1 - y : y, policy);
                 }
+                ++i;
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        // Warp-uniform control flow; one elected lane issues.  The issuing thread is the scarce
-        // resource (13+ MMAs, 2 waits and 2 commits per ~1150 tensor-pipe cycles), so interior rows
-        // take a straight-line path whose descriptors differ from per-row bases by constants only.
+        // Warp-uniform control flow; one elected lane issues.  The tensor pipe's instruction queue is
+        // shallow, so the barriers of the next step are polled in the middle of the current one.
         mbar_wait(base + kBarW, 0, dbg, TAG_W);
-        tc_fence_after();
-        const uint32_t idesc1 = umma_idesc_f16(128, NG);
-        const uint32_t idesc2 = umma_idesc_f16(128, 2 * NG);
-        const uint32_t idesc3 = umma_idesc_f16(128, 3 * NG);
-        const uint64_t proto = umma_desc_sw128(0, 0);
-        const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
-        const uint32_t lo_flags = static_cast<uint32_t>(proto);              // LBO field
-        const uint32_t w_lo = lo_flags | ((base + kOffW) >> 4);
-        const uint32_t ring_lo = lo_flags | ((base + kOffRing) >> 4);
-        constexpr uint32_t kG = NG * 8;        // one group of B rows, in 16-byte units
-        constexpr uint32_t kDx = 3 * NG * 8;   // one dx block of B
-                // Issue helpers (called by the elected lane only).  Part 1 = first K-step (the fresh group
-        // overwrites, the others accumulate) plus three more K-steps; part 2 = the other eight.
-        // MMAs that read the same A tile back to back keep it in the tensor core's collector buffer
-        // (FILL ... LASTUSE) instead of re-reading shared memory: that makes the split MMAs of the
-        // ring-wrap rows (N=128 + N=64) cost the same tensor time as one N=192 MMA.
-        auto issue_part1 = [&](uint32_t a_lo, int s0, uint32_t w_lo) {
-            const uint64_t a0 = mk_desc(desc_hi, a_lo - 8);
-            const uint32_t d = tmem_base + s0 * NG;
-            if (s0 <= 5) {
-                umma_f16_a<ACollector::FILL>(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                umma_f16_a<ACollector::LASTUSE>(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
-#pragma unroll
-                for (int dxk = 1; dxk < 4; ++dxk)
-                    umma_f16(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_lo + dxk * 2), idesc3, 1u);
-            } else if (s0 == 6) {
-                umma_f16_a<ACollector::FILL>(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                umma_f16_a<ACollector::USE>(d + NG, a0, mk_desc(desc_hi, w_lo + kG), idesc1, 1u);
-                umma_f16_a<ACollector::LASTUSE>(tmem_base, a0, mk_desc(desc_hi, w_lo + 2 * kG), idesc1, 1u);
-#pragma unroll
-                for (int dxk = 1; dxk < 4; ++dxk) {
-                    const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
-                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc2, 1u);
-                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + 2 * kG), idesc1, 1u);
-                }
+        if constexpr (PAIR) {
+            if (!leader) {
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(base + kBarWPeer, 0));
             } else {
-                umma_f16_a<ACollector::FILL>(d, a0, mk_desc(desc_hi, w_lo), idesc1, 0u);
-                umma_f16_a<ACollector::LASTUSE>(tmem_base, a0, mk_desc(desc_hi, w_lo + kG), idesc2, 1u);
-#pragma unroll
-                for (int dxk = 1; dxk < 4; ++dxk) {
-                    const uint64_t ad = mk_desc(desc_hi, a_lo - 8 + dxk * 2);
-                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dxk * 2), idesc1, 1u);
-                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dxk * 2 + kG), idesc2, 1u);
-                }
+                mbar_wait(base + kBarWPeer, 0, dbg, TAG_W_PEER);
             }
-        };
-        auto issue_part2 = [&](uint32_t a_lo, int s0, uint32_t w_lo) {
-            const uint32_t d = tmem_base + s0 * NG;
-            if (s0 <= 5) {
-#pragma unroll
-                for (int dxk = 4; dxk < 12; ++dxk) {
-                    const int dx = dxk >> 2, k = dxk & 3;
-                    umma_f16(d, mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2), mk_desc(desc_hi, w_lo + dx * kDx + k * 2),
-                             idesc3, 1u);
-                }
-            } else if (s0 == 6) {
-#pragma unroll
-                for (int dxk = 4; dxk < 12; ++dxk) {
-                    const int dx = dxk >> 2, k = dxk & 3;
-                    const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc2, 1u);
-                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + 2 * kG), idesc1, 1u);
-                }
-            } else {
-#pragma unroll
-                for (int dxk = 4; dxk < 12; ++dxk) {
-                    const int dx = dxk >> 2, k = dxk & 3;
-                    const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                    umma_f16_a<ACollector::FILL>(d, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2), idesc1, 1u);
-                    umma_f16_a<ACollector::LASTUSE>(tmem_base, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + kG), idesc2, 1u);
-                }
-            }
-        };
-        // Edge rows of a segment (first / last two input rows): one MMA per group and K-step.
-        auto edge_row = [&](int y, int ya, int yb, uint32_t i, int t0) {
-            const uint32_t stage = i % kStages, use = i / kStages;
-            const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
-            const int s0 = (-t0) & 7;
-            // group g (0..2) = vertical tap: input row y feeds output row y + 1 - g
-            const int g_lo = (y + 1 <= yb) ? 0 : ((y <= yb) ? 1 : 2);
-            const int g_hi = (y - 1 >= ya) ? 2 : ((y >= ya) ? 1 : 0);
-            // groups whose output row receives its first contribution from this input row
-            const int fresh_hi = (y == 0) ? g_hi : ((g_lo == 0) ? 0 : g_lo - 1);
-            for (int g = g_lo; g <= fresh_hi; ++g) {
-                const int tg = t0 - g;
-                mbar_wait(base + kBarAccEmpty + 8 * ((s0 + g) & 7), ((tg >> 3) & 1) ^ 1, dbg, TAG_ACC_EMPTY, tg);
-            }
-            mbar_wait(base + kBarAFull + 8 * stage, use & 1, dbg, TAG_A_FULL, i);
+        }
+        if (leader) {
             tc_fence_after();
-            if (elect_one()) {
-                for (int dxk = 0; dxk < 12; ++dxk) {
-                    const int dx = dxk >> 2, k = dxk & 3;
-                    const uint64_t ad = mk_desc(desc_hi, a_lo + (dx - 1) * 8 + k * 2);
-                    for (int g = g_lo; g <= g_hi; ++g)
-                        umma_f16(tmem_base + ((s0 + g) & 7) * NG, ad, mk_desc(desc_hi, w_lo + dx * kDx + k * 2 + g * kG),
-                                 idesc1, (dxk == 0 && g <= fresh_hi) ? 0u : 1u);
+            const uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, 3 * NG);
+            const uint64_t proto = umma_desc_sw128(0, 0);
+            const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
+            const uint32_t lo_flags = static_cast<uint32_t>(proto);              // LBO field
+            const uint32_t w_lo = lo_flags | ((base + kOffW) >> 4);
+            const uint32_t ring_lo = lo_flags | ((base + kOffRing) >> 4);
+            constexpr uint32_t kDx = kRowsDx * 8;   // one dx block of B, in 16-byte units
+            constexpr uint32_t kRot = NG * 8;       // one weight group
+
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b) {
+                if constexpr (PAIR) umma_f16_pair(d, a, b, idesc, 1u); else umma_f16(d, a, b, idesc, 1u);
+            };
+            auto commit = [&](uint32_t bar) {
+                if constexpr (PAIR) umma_commit_pair(bar, 3); else umma_commit(bar);
+            };
+            // barriers a step has to pass before its MMAs may be issued
+            struct Gate { uint32_t bar_f, par_f, bar_e, par_e; bool need_e; };
+            auto gate_of = [&](uint32_t i, int s, int k) {
+                Gate g;
+                g.bar_f = base + kBarAFull + 8 * (i % kStages);
+                g.par_f = (i / kStages) & 1;
+                // fresh slot of step k = slot of event k+1, last used by event k-2
+                g.need_e = k >= 2;
+                g.bar_e = base + kBarAccEmpty + 8 * (s * 3 + (k + 1) % 3);
+                g.par_e = ((k - 2) / 3) & 1;
+                return g;
+            };
+            Sequencer seq(U[0], U[1]);
+            uint32_t i = 0;
+            bool have = seq.next();
+            if (have) {
+                const Gate g = gate_of(0, seq.s, seq.k);
+                mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, 0);
+                tc_fence_after();
+            }
+            const bool elected = elect_one();
+            while (have) {
+                const int s = seq.s, k = seq.k;
+                const uint32_t stage = i % kStages;
+                const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
+                // event k+1-g (vertical tap g) lives in slot (k+1-g) mod 3: B starts (2 - (k+1) mod 3) groups into the blob
+                uint32_t w_row = w_lo + (2 - (k + 1) % 3) * kRot;
+                asm volatile("" : "+r"(w_row));   // keep the 12 B descriptors as adds on one per-step value
+                const uint32_t d = tmem_base + s * kBank;
+                if (p.trace && blockIdx.x == 0 && i < 1000 && lane == 0) p.trace[i] = clock64();
+                if (elected) {
+#pragma unroll
+                    for (int dxk = 0; dxk < 4; ++dxk)
+                        mma(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_row + dxk * 2));
                 }
-                if (i & 1u) umma_commit(base + kBarAEmpty + 8 * ((i >> 1) % (kStages / 2)));  // rows i-1, i retired
-                if (g_hi == 2) umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));  // row y-1 complete
-                if (y == CH - 1 && yb == CH - 1)                                       // bottom edge: row y too
-                    umma_commit(base + kBarAccFull + 8 * ((s0 + 1) & 7));
+                // look ahead: barriers of the next step
+                have = seq.next();
+                Gate g{};
+                bool ok = true;
+                if (have) {
+                    g = gate_of(i + 1, seq.s, seq.k);
+                    ok = mbar_try_wait(g.bar_f, g.par_f);
+                    if (g.need_e) ok = mbar_try_wait(g.bar_e, g.par_e) && ok;
+                }
+                if (elected) {
+#pragma unroll
+                    for (int dxk = 4; dxk < 12; ++dxk) {
+                        const int dx = dxk >> 2, kk = dxk & 3;
+                        mma(d, mk_desc(desc_hi, a_lo + (dx - 1) * 8 + kk * 2), mk_desc(desc_hi, w_row + dx * kDx + kk * 2));
+                    }
+                    commit(base + kBarAEmpty + 8 * stage);                       // ring slot consumed
+                    commit(base + kBarAccFull + 8 * (s * 3 + (k - 1) % 3));      // event k-1 complete
+                }
+                if (!ok) {
+                    if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1000] += 1;   // look-ahead misses
+                    mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, i + 1);
+                    if (g.need_e) mbar_wait(g.bar_e, g.par_e, dbg, TAG_ACC_EMPTY, seq.k);
+                }
+                tc_fence_after();
+                ++i;
             }
             __syncwarp();
-        };
-
-        SegIter it(p);
-        int strip, ya, yb;
-        uint32_t i = 0;   // input rows issued so far (ring stage = i mod kStages)
-        int t_base = 0;   // output rows of earlier segments
-        while (it.next(strip, ya, yb)) {
-            const int y_lo = max(ya - 1, 0), y_hi = min(yb + 1, CH - 1);
-            int y = y_lo;
-            for (; y <= min(ya, y_hi); ++y, ++i) edge_row(y, ya, yb, i, t_base + (y + 1 - ya));
-            // ---- interior rows ya+1 .. yb-1: groups 0..2 enabled, only group 0 fresh, row y-1 completes.
-            // The tensor pipe's instruction queue is shallow: every cycle the issuing thread spends on
-            // anything else between two rows is a bubble.  So the barriers of row y+1 are polled in the
-            // middle of row y, and the loop carries only (i, t0).
-            int n_int = yb - ya - 1;
-            if (n_int > 0) {
-                int t0 = t_base + 2;  // y = ya + 1
-                {
-                    const int s0 = (-t0) & 7;
-                    mbar_wait(base + kBarAccEmpty + 8 * s0, ((t0 >> 3) & 1) ^ 1, dbg, TAG_ACC_EMPTY, t0);
-                    mbar_wait(base + kBarAFull + 8 * (i % kStages), (i / kStages) & 1, dbg, TAG_A_FULL, i);
-                    tc_fence_after();
-                }
-                const bool leader = elect_one();
-                for (; n_int > 0; --n_int, ++i, ++t0, ++y) {
-                    const uint32_t stage = i % kStages;
-                    const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
-                    const int s0 = (-t0) & 7;
-                    long long* const tr = (p.trace && blockIdx.x == 0 && i < 256) ? p.trace + i * 4 : nullptr;
-                    if (tr && lane == 0) { tr[0] = clock64(); tr[3] = s0 << 4; }
-                    // Opaque per-row copy of the weight descriptor base: keeps the compiler from hoisting 36
-                    // loop-invariant B descriptors into vector registers (two R2UR moves per MMA); the
-                    // descriptors become uniform-datapath adds on one per-row value instead.
-                    uint32_t w_row = w_lo;
-                    asm volatile("" : "+r"(w_row));
-                    if (leader) issue_part1(a_lo, s0, w_row);
-                    // look ahead: barriers of the next interior row
-                    bool ok = true;
-                    uint32_t bar_e = 0, par_e = 0, bar_f = 0, par_f = 0;
-                    if (n_int > 1) {
-                        bar_e = base + kBarAccEmpty + 8 * ((s0 + 7) & 7);
-                        par_e = (((t0 + 1) >> 3) & 1) ^ 1;
-                        bar_f = base + kBarAFull + 8 * ((i + 1) % kStages);
-                        par_f = ((i + 1) / kStages) & 1;
-                        const bool ok_e = mbar_try_wait(bar_e, par_e);
-                        const bool ok_f = mbar_try_wait(bar_f, par_f);
-                        ok = ok_e && ok_f;
-                    }
-                    if (tr && lane == 0) tr[1] = clock64();
-                    if (leader) {
-                        issue_part2(a_lo, s0, w_row);
-                        if (i & 1u) umma_commit(base + kBarAEmpty + 8 * ((i >> 1) % (kStages / 2)));
-                        umma_commit(base + kBarAccFull + 8 * ((s0 + 2) & 7));
-                    }
-                    if (!ok) {
-                        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[2040] += 1;   // look-ahead misses
-                        mbar_wait(bar_e, par_e, dbg, TAG_ACC_EMPTY, t0 + 1);
-                        mbar_wait(bar_f, par_f, dbg, TAG_A_FULL, i + 1);
-                    }
-                    tc_fence_after();
-                    if (tr && lane == 0) tr[2] = clock64();
-                    if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[2041] += 1;       // interior rows
-                }
-                __syncwarp();
-            }
-            for (; y <= y_hi; ++y, ++i) edge_row(y, ya, yb, i, t_base + (y + 1 - ya));
-            t_base += yb - ya + 1;
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
-        const int grp = (warp - 2) >> 2;   // group 0 / 1 take even / odd output-row sequence numbers
+        const int grp = (warp - 2) >> 2;   // group = stream
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;       // M row = pixel index inside the 128-px box
-        const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        SegIter it(p);
-        int strip, ya, yb;
-        int t = 0;
-        while (it.next(strip, ya, yb)) {
-            const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
-            const int cx = x0 - 1 + m;
-            const bool inside = (m >= 1) && (m <= kStripPx) && (cx < p.canvas_w);
-            const bool colok = inside && (p.colflag[cx] != 0);
-            int ox = -1, sx = 0;
-            if (TAIL && inside) {
-                ox = p.out_x[cx];
-                sx = p.src_x[cx];
+        const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * kBank;
+        const uint32_t empty_base = PAIR ? mapa_u32(base + kBarAccEmpty + 8 * grp * 3, 0) : (base + kBarAccEmpty + 8 * grp * 3);
+        long long lo, hi;
+        stream_range<PAIR>(p, rank, grp, lo, hi);
+        Cursor cur(lo, hi, CH);
+        const int n_events = U[grp];   // events 0 .. U-1 (event e is completed by step e+1)
+        int x0 = 0, ox = -1, sx = 0;
+        bool colok = false;
+        for (int e = 0; e < n_events; ++e) {
+            bool valid = false;
+            int y = 0;
+            if (e >= 1) {
+                int strip;
+                bool newseg;
+                valid = cur.next(strip, y, newseg);
+                if (newseg) {
+                    x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
+                    const int cx = x0 - 1 + m;
+                    const bool inside = (m >= 1) && (m <= kStripPx) && (cx < p.canvas_w);
+                    colok = inside && (p.colflag[cx] != 0);
+                    ox = -1;
+                    if (TAIL && inside) {
+                        ox = p.out_x[cx];
+                        sx = p.src_x[cx];
+                    }
+                }
             }
-            for (int r = ya; r <= yb; ++r, ++t) {
-                if ((t & 1) != grp) continue;
-                const int pr = rev ? CH - 1 - r : r;  // physical canvas row
-                const int s = (-t) & 7;
-                long long* const tr = (p.trace && blockIdx.x == 0 && t < 256 && q == 0 && lane == 0)
-                                          ? p.trace + 1024 + t * 4 : nullptr;
-                if (tr) tr[0] = clock64();
-                mbar_wait(base + kBarAccFull + 8 * s, (t >> 3) & 1, dbg, TAG_ACC_FULL, t);
-                if (tr) tr[1] = clock64();
-                tc_fence_after();
-                uint32_t acc[NG];
+            const int pr = rev ? CH - 1 - y : y;  // physical canvas row
+            const int slot = e % 3;
+            long long* const tr = (p.trace && blockIdx.x == 0 && grp == 0 && e < 256 && q == 0 && lane == 0)
+                                      ? p.trace + 1024 + e * 4 : nullptr;
+            if (tr) tr[0] = clock64();
+            mbar_wait(base + kBarAccFull + 8 * (grp * 3 + slot), (e / 3) & 1, dbg, TAG_ACC_FULL, e);
+            if (tr) tr[1] = clock64();
+            tc_fence_after();
+            uint32_t acc[NG];
+            if (valid) {
 #pragma unroll
                 for (int c = 0; c < NG / 16; ++c) {
                     uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
-                    tmem_ld16(tmem_lane + s * NG + c * 16, dst);
+                    tmem_ld16(tmem_lane + slot * NG + c * 16, dst);
                 }
                 tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(base + kBarAccEmpty + 8 * s);
-                if (tr) tr[2] = clock64();
+            }
+#pragma unroll
+            for (int c = 0; c < NG / 16; ++c) tmem_st16_fill(tmem_lane + slot * NG + c * 16, 0u);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(empty_base + 8 * slot); else mbar_arrive(empty_base + 8 * slot);
+            }
+            if (tr) tr[2] = clock64();
+            if (!valid) continue;
 
-                if constexpr (!TAIL) {
-                    const bool keep = colok && (p.rowflag[pr] != 0);
-                    const uint32_t stg = base + kOffStage + grp * kRowBytes;
-                    const bool gleader = (q == 0 && lane == 0);
-                    if (gleader) bulk_wait_read<0>();   // this group's previous row has left the staging buffer
-                    named_bar_sync(1 + grp, 128);
-                    if (m >= 1 && m <= kStripPx) {
-                        const int row = m - 1;
-                        const uint32_t rbase = stg + row * 128;
-                        if (keep) {
+            if constexpr (!TAIL) {
+                const bool keep = colok && (p.rowflag[pr] != 0);
+                const uint32_t stg = base + kOffStage + grp * kRowBytes;
+                const bool gleader = (q == 0 && lane == 0);
+                if (gleader) bulk_wait_read<0>();   // this group's previous row has left the staging buffer
+                named_bar_sync(1 + grp, 128);
+                if (m >= 1 && m <= kStripPx) {
+                    const int row = m - 1;
+                    const uint32_t rbase = stg + row * 128;
+                    if (keep) {
 #pragma unroll
-                            for (int c8 = 0; c8 < 8; ++c8) {
-                                uint32_t pk[4];
+                        for (int c8 = 0; c8 < 8; ++c8) {
+                            uint32_t pk[4];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int ch = c8 * 8 + j * 2;
-                                    // bias in fp32, then PReLU on the packed fp16 pair: max(v,0) + a*min(v,0).
-                                    // Positive values are bit-identical to the fp32 formulation; negative ones
-                                    // round twice (<= 1 ulp of fp16 instead of 0.5).
-                                    const __half2 v = __floats2half2_rn(__uint_as_float(acc[ch]) + p.bias[ch],
-                                                                        __uint_as_float(acc[ch + 1]) + p.bias[ch + 1]);
-                                    const __half2 z = __float2half2_rn(0.f);
-                                    const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
-                                    pk[j] = *reinterpret_cast<const uint32_t*>(&r);
-                                }
-                                st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            for (int j = 0; j < 4; ++j) {
+                                const int ch = c8 * 8 + j * 2;
+                                // bias in fp32, then PReLU on the packed fp16 pair: max(v,0) + a*min(v,0).
+                                // Positive values are bit-identical to the fp32 formulation; negative ones
+                                // round twice (<= 1 ulp of fp16 instead of 0.5).
+                                const __half2 v = __floats2half2_rn(__uint_as_float(acc[ch]) + p.bias[ch],
+                                                                    __uint_as_float(acc[ch + 1]) + p.bias[ch + 1]);
+                                const __half2 z = __float2half2_rn(0.f);
+                                const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                                pk[j] = *reinterpret_cast<const uint32_t*>(&r);
                             }
-                        } else {   // gap pixel (between tiles / frames): must read as zero in the next layer
-#pragma unroll
-                            for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + (c8 << 4), 0u, 0u, 0u, 0u);
+                            st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                         }
+                    } else {   // gap pixel (between tiles / frames): must read as zero in the next layer
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + (c8 << 4), 0u, 0u, 0u, 0u);
                     }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + grp, 128);
-                    if (gleader) {
-                        tma_store_3d(&out_map, stg, 0, x0, pr);
-                        bulk_commit();
-                    }
-                } else {
-                    constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
-                    const int oy = p.out_y[pr];
-                    if (ox >= 0 && oy >= 0) {
-                        const int fr = p.row_frame[pr];
-                        const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
-                        const float xin[3] = {static_cast<float>(sp[0]), static_cast<float>(sp[1]),
-                                              static_cast<float>(sp[2])};
-                        // S*3 consecutive bytes per output row: packed into 16-/32-bit stores when aligned
-                        const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + grp, 128);
+                if (gleader) {
+                    tma_store_3d(&out_map, stg, 0, x0, pr);
+                    bulk_commit();
+                }
+                if (tr) tr[3] = clock64();
+            } else {
+                constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
+                const int oy = p.out_y[pr];
+                if (ox >= 0 && oy >= 0) {
+                    const int fr = p.row_frame[pr];
+                    const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
+                    const float xin[3] = {static_cast<float>(sp[0]), static_cast<float>(sp[1]),
+                                          static_cast<float>(sp[2])};
+                    // S*3 consecutive bytes per output row: packed into 16-/32-bit stores when aligned
+                    const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
 #pragma unroll
-                        for (int i = 0; i < S; ++i) {
-                            uint8_t* dp = p.dst[fr] + static_cast<long long>(oy * S + i) * p.dst_stride +
-                                          static_cast<long long>(ox) * (S * 3);
-                            uint32_t b[S * 3];
+                    for (int i = 0; i < S; ++i) {
+                        uint8_t* dp = p.dst[fr] + static_cast<long long>(oy * S + i) * p.dst_stride +
+                                      static_cast<long long>(ox) * (S * 3);
+                        uint32_t b[S * 3];
 #pragma unroll
-                            for (int j = 0; j < S; ++j) {
+                        for (int j = 0; j < S; ++j) {
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    const int idx = c * S * S + i * S + j;
-                                    const float v = __uint_as_float(acc[idx]) +
-                                                    reinterpret_cast<const float*>(base_ptr + kOffBias)[idx];
-                                    // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5))
-                                    float o = floorf(fmaf(v, 255.f, xin[c] + 0.5f));
-                                    o = fminf(fmaxf(o, 0.f), 255.f);
-                                    b[j * 3 + c] = static_cast<uint32_t>(o);
-                                }
+                            for (int c = 0; c < 3; ++c) {
+                                const int idx = c * S * S + i * S + j;
+                                const float v = __uint_as_float(acc[idx]) +
+                                                reinterpret_cast<const float*>(base_ptr + kOffBias)[idx];
+                                // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5))
+                                float o = floorf(fmaf(v, 255.f, xin[c] + 0.5f));
+                                o = fminf(fmaxf(o, 0.f), 255.f);
+                                b[j * 3 + c] = static_cast<uint32_t>(o);
                             }
-                            if (wide && S == 2) {
-                                uint16_t* d16 = reinterpret_cast<uint16_t*>(dp);   // 6*ox: 2-byte aligned
+                        }
+                        if (wide && S == 2) {
+                            uint16_t* d16 = reinterpret_cast<uint16_t*>(dp);   // 6*ox: 2-byte aligned
 #pragma unroll
-                                for (int k = 0; k < 3; ++k) d16[k] = static_cast<uint16_t>(b[2 * k] | (b[2 * k + 1] << 8));
-                            } else if (wide && S == 4) {
-                                uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);   // 12*ox: 4-byte aligned
+                            for (int k = 0; k < 3; ++k) d16[k] = static_cast<uint16_t>(b[2 * k] | (b[2 * k + 1] << 8));
+                        } else if (wide && S == 4) {
+                            uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);   // 12*ox: 4-byte aligned
 #pragma unroll
-                                for (int k = 0; k < 3; ++k)
-                                    d32[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
-                            } else {
+                            for (int k = 0; k < 3; ++k)
+                                d32[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
+                        } else {
 #pragma unroll
-                                for (int k = 0; k < S * 3; ++k) dp[k] = static_cast<uint8_t>(b[k]);
-                            }
+                            for (int k = 0; k < S * 3; ++k) dp[k] = static_cast<uint8_t>(b[k]);
                         }
                     }
                 }
@@ -471,37 +522,46 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 
     if (!TAIL && warp >= 2 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
-template <int NG, bool TAIL>
+template <int NG, bool TAIL, bool PAIR>
 constexpr size_t smem_bytes_t() {
-    return 1024 /*alignment slack*/ + kCtrlBytes + w_bytes(NG) + kGuard + kStages * kRowBytes + kGuard +
-           (TAIL ? 0 : 2 * kRowBytes);
+    return 1024 /*alignment slack*/ + kCtrlBytes + w_smem_bytes(NG, PAIR) + kGuard +
+           ring_stages(NG, TAIL, PAIR) * kRowBytes + kGuard + (TAIL ? 0 : 2 * kRowBytes);
+}
+
+template <int NG, bool TAIL, bool PAIR>
+cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(conv3x3_umma_kernel<NG, TAIL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem_bytes_t<NG, TAIL, PAIR>()));
 }
 
 }  // namespace
 
-size_t conv_weight_blob_bytes(int ng) { return w_bytes(ng); }
+size_t conv_weight_blob_bytes(int ng) { return w_smem_bytes(ng, false); }
 
 void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16_t* blob) {
-    // blob[dx][n = g*ng + o][ci] fp16 with the 128-byte swizzle applied per 128-byte row:
-    // 16-byte chunk c of row n is stored at chunk (c ^ (n & 7)).  Group g holds vertical tap
-    // ky = g (forward sweep) or ky = 2 - g (reverse sweep).
-    std::memset(blob, 0, w_bytes(ng));
+    // blob[dx][n over 5 blocks of ng rows][ci] fp16 with the 128-byte swizzle applied per 128-byte row:
+    // 16-byte chunk c of row n is stored at chunk (c ^ (n & 7)).  Block j holds weight group
+    // g = (2 - j) mod 3, i.e. [W2|W1|W0|W2|W1], so the three cyclic rotations the rotating accumulator
+    // bank needs are start offsets of 0, 1, 2 blocks.  Group g holds vertical tap ky = g (forward sweep)
+    // or ky = 2 - g (reverse sweep).
+    std::memset(blob, 0, conv_weight_blob_bytes(ng));
     for (int dx = 0; dx < 3; ++dx)
-        for (int g = 0; g < 3; ++g)
+        for (int j = 0; j < 5; ++j)
             for (int o = 0; o < co; ++o) {
-                const int n = g * ng + o;
+                const int g = ((2 - j) % 3 + 3) % 3;
+                const int n = j * ng + o;
                 const int ky = reverse ? 2 - g : g;
                 for (int ci = 0; ci < 64; ++ci) {
                     const float v = w_oihw[((static_cast<size_t>(o) * 64 + ci) * 3 + ky) * 3 + dx];
-                    const size_t byte = static_cast<size_t>(dx) * (3 * ng * 128) + static_cast<size_t>(n) * 128 +
+                    const size_t byte = static_cast<size_t>(dx) * (5 * ng * 128) + static_cast<size_t>(n) * 128 +
                                         (((ci >> 3) ^ (n & 7)) << 4) + (ci & 7) * 2;
                     blob[byte / 2] = f32_to_f16(v);
                 }
@@ -510,31 +570,39 @@ void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16
 
 cudaError_t conv_kernels_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(conv3x3_umma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<64, false>()));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(conv3x3_umma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<16, true>()));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(conv3x3_umma_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<32, true>()));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(conv3x3_umma_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes_t<48, true>()));
-    return e;
+    if ((e = set_smem_attr<64, false, false>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<64, false, true>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<16, true, false>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<32, true, false>()) != cudaSuccess) return e;
+    return set_smem_attr<48, true, false>();
 }
 
-cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
+cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map,
                              const ConvParams& p) {
-    conv3x3_umma_kernel<64, false><<<grid, kConvThreads, smem_bytes_t<64, false>(), st>>>(in_map, out_map, p);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid & ~1), 1, 1);
+        cfg.blockDim = dim3(kConvThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem_bytes_t<64, false, true>();
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<64, false, true>, in_map, out_map, p);
+    }
+    conv3x3_umma_kernel<64, false, false><<<grid, kConvThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p) {
     switch (scale) {
-        case 2: conv3x3_umma_kernel<16, true><<<grid, kConvThreads, smem_bytes_t<16, true>(), st>>>(in_map, in_map, p); break;
-        case 3: conv3x3_umma_kernel<32, true><<<grid, kConvThreads, smem_bytes_t<32, true>(), st>>>(in_map, in_map, p); break;
-        case 4: conv3x3_umma_kernel<48, true><<<grid, kConvThreads, smem_bytes_t<48, true>(), st>>>(in_map, in_map, p); break;
+        case 2: conv3x3_umma_kernel<16, true, false><<<grid, kConvThreads, smem_bytes_t<16, true, false>(), st>>>(in_map, in_map, p); break;
+        case 3: conv3x3_umma_kernel<32, true, false><<<grid, kConvThreads, smem_bytes_t<32, true, false>(), st>>>(in_map, in_map, p); break;
+        case 4: conv3x3_umma_kernel<48, true, false><<<grid, kConvThreads, smem_bytes_t<48, true, false>(), st>>>(in_map, in_map, p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

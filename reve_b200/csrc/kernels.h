@@ -10,7 +10,6 @@ namespace reve {
 
 constexpr int kBoxPx = 128;    // pixels per TMA row box = UMMA M
 constexpr int kStripPx = 126;  // valid output pixels per strip row (box minus the 2 halo columns)
-constexpr int kStages = 6;     // A-row ring depth (released to the producer in pairs)
 constexpr int kMaxBatch = 4;    // frames stacked on one canvas per launch (gap row between frames)
 constexpr int kConvThreads = 320;  // producer warp + MMA warp + 2 x 4 epilogue warps
 
@@ -26,6 +25,7 @@ struct ConvParams {
     const void* weights;        // pre-swizzled B operand blob of this layer (global memory)
     __half* out;                // body: output canvas [canvas_h][canvas_w][64] fp16
     int reverse;                // sweep the strip-rows bottom-up (weights blob packed accordingly)
+    uint32_t flags;             // debug: bit0 = CTA pair loads the other half of B
     DebugBlock* dbg;            // mapped pinned host memory, may be null
     long long* trace;           // debug timeline of CTA 0 (device memory, may be null)
     // tail only
@@ -63,7 +63,8 @@ size_t conv_weight_blob_bytes(int ng);
 void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16_t* blob);
 
 cudaError_t conv_kernels_init();  // opt-in shared memory attributes; call once per device
-cudaError_t launch_conv_body(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
+// `pair`: launch as clusters of two CTAs driving tcgen05.mma.cta_group::2 (grid rounded down to even)
+cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p);
 size_t conv0_weight_blob_bytes();
 void pack_conv0_weights(const float* w_oihw, uint16_t* blob);

@@ -1,5 +1,9 @@
-"""Dump the per-row timeline of CTA 0 of body layer 5 (REVE_DEBUG_TRACE).  GPU box only."""
-import ctypes as C
+"""Dump the per-step timeline of CTA 0 of body layer 5 (REVE_DEBUG_TRACE).  GPU box only.
+
+trace[0..999]   clock at the start of MMA step i (interleaved order of the CTA's two streams)
+trace[1000]     look-ahead misses
+trace[1024+4e]  epilogue group 0, event e: wait start, accumulator full, slot handed back, row stored
+"""
 import os
 import sys
 
@@ -19,18 +23,19 @@ for _ in range(3):
 tr = np.zeros(2048, np.int64)
 rc = _lib.load().reve_debug_trace(up._h, tr.ctypes.data, 2048)
 assert rc == 0
-print("look-ahead misses / interior rows (3 frames, CTA 0 of layer 5):", tr[2040], "/", tr[2041])
-mma = tr[:1024].reshape(256, 4)
+steps = tr[:1000]
+steps = steps[steps > 0]
+d = np.diff(steps)
+print(f"flags={os.environ.get('REVE_DEBUG_FLAGS', '0')} steps traced: {len(steps)}  look-ahead misses: {tr[1000]}")
+if len(d):
+    core = d[4:-4] if len(d) > 16 else d
+    print(f"clk/step: mean {core.mean():.1f}  median {np.median(core):.1f}  p10 {np.percentile(core, 10):.0f}  p90 {np.percentile(core, 90):.0f}  max {core.max()}")
+    print("first 40 step deltas:", d[:40].tolist())
 epi = tr[1024:].reshape(256, 4)
-t0 = mma[mma[:, 0] > 0][:, 0].min()
-print("row  start  waited  issued | flags(s0,okF,okE) | epi: wait_start got_full arrived  (cycles rel. to first MMA row)")
-prev = None
-for i in range(0, 150):
-    if mma[i, 0] == 0:
+t0 = steps[0] if len(steps) else 0
+print("event  wait_start  got_full  released  stored   (cycles rel. to first MMA step)")
+for e in range(0, 40):
+    a, b, c, s = epi[e]
+    if a == 0:
         continue
-    a, b, c, f = mma[i]
-    d = (a - prev) if prev is not None else 0
-    prev = a
-    t = i - 1
-    e = epi[t] if 0 <= t < 256 else [0, 0, 0, 0]
-    print(f"{i:3d} {a - t0:7d} {b - a:6d} {c - b:6d}  dRow={d:5d} | s0={f >> 4} okF={(f >> 1) & 1} okE={f & 1} | t={t:3d} {e[0] - t0:8d} {e[1] - t0:8d} {e[2] - t0:8d}")
+    print(f"{e:5d} {a - t0:10d} {b - t0:9d} {c - t0:9d} {(s - t0) if s else 0:8d}")

@@ -1,0 +1,120 @@
+// Micro-benchmark v5: tcgen05.mma.cta_group::2 (CTA pair, M = 256) issue / execution rate for the body
+// kernel's MMA pattern: 12 MMAs per row (3 horizontal taps x 4 K-steps), N = 192 or 256, SW128 K-major.
+// Question: does the pair form run at N/2 clk per MMA like cta_group::1 M=128, and what do shifted A
+// descriptors, commits and the B block stride cost?
+//   mode bit0: pair (cta_group::2, M=256)      bit1: N=256 instead of 192      bit2: aligned A only
+//   mode bit3: two multicast commits per row   bit4: alternate two accumulator banks (like two streams)
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "ptx.cuh"
+using namespace reve;
+struct Result { long long cycles; int rows; float sample[4]; };
+__device__ __forceinline__ uint64_t mk(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+template <bool PAIR>
+__global__ void __launch_bounds__(128, 1) bench(int mode, int rows, Result* res) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* bp = smem_raw + (base - raw);
+    constexpr uint32_t kW = 3 * 256 * 128;   // room for 3 dx blocks of 256 rows
+    const uint32_t w_addr = base + 1024, ring = base + 1024 + kW + 1024;
+    for (uint32_t i = threadIdx.x; i < (kW + 1024 + 6 * 16384 + 1024) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(bp + 1024)[i] = 0x3c003c00u;   // fp16 1.0
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    if (threadIdx.x == 0) { mbar_init(base, 1); mbar_init(base + 8, 1); mbar_init(base + 16, 1); fence_mbar_init(); }
+    if (warp == 0) {
+        if constexpr (PAIR) { tmem_alloc_pair(base + 512, 512); tmem_relinquish_pair(); }
+        else { tmem_alloc(base + 512, 512); tmem_relinquish(); }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(bp + 512);
+    const bool n256 = mode & 2, aligned = mode & 4, commits = mode & 8, banks = mode & 16;
+    if (warp == 0 && rank == 0) {
+        const uint64_t proto = umma_desc_sw128(0, 0);
+        const uint32_t desc_hi = (uint32_t)(proto >> 32), lof = (uint32_t)proto;
+        const uint32_t w_lo = lof | (w_addr >> 4), ring_lo = lof | (ring >> 4);
+        const int N = n256 ? 256 : 192;
+        const uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, N);
+        const uint32_t kDx = (PAIR ? N / 2 + 32 : N + 64) * 8;
+        long long t0 = clock64();
+        if (elect_one()) {
+            for (int r = 0; r < rows; ++r) {
+                const uint32_t a_lo = ring_lo + (r % 6) * 1024;
+                const uint32_t d = tmem_base + ((banks && (r & 1)) ? 256 : 0);
+#pragma unroll
+                for (int dxk = 0; dxk < 12; ++dxk) {
+                    const int dx = dxk >> 2, k = dxk & 3;
+                    const uint64_t ad = mk(desc_hi, a_lo + (aligned ? 0 : (dx - 1) * 8) + k * 2);
+                    const uint64_t bd = mk(desc_hi, w_lo + dx * kDx + k * 2);
+                    const uint32_t acc = (r > 1 || dxk) ? 1u : 0u;
+                    if constexpr (PAIR) umma_f16_pair(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+                }
+                if (commits) {
+                    if constexpr (PAIR) { umma_commit_pair(base + 8, 3); umma_commit_pair(base + 16, 3); }
+                    else { umma_commit(base + 8); umma_commit(base + 16); }
+                }
+            }
+            if constexpr (PAIR) umma_commit_pair(base, 1); else umma_commit(base);
+        }
+        __syncwarp();
+        mbar_wait(base, 0, nullptr, 0);
+        const long long t1 = clock64();
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16(tmem_base + 0, v);
+        tmem_wait_ld();
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            res->cycles = t1 - t0; res->rows = rows;
+            res->sample[0] = __uint_as_float(v[0]);
+        }
+    }
+    tc_fence_before();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static cudaError_t launch(int mode, int rows, Result* d, int smem) {
+    if (mode & 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, bench<true>, mode, rows, d);
+    }
+    bench<false><<<148, 128, smem>>>(mode, rows, d);
+    return cudaGetLastError();
+}
+
+int main() {
+    const int smem = 1024 + 1024 + 3 * 256 * 128 + 1024 + 6 * 16384 + 1024;
+    cudaFuncSetAttribute(bench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    Result* d; cudaMalloc(&d, sizeof(Result));
+    for (int w = 0; w < 50; ++w) launch(0, 1200, d, smem);
+    cudaDeviceSynchronize();
+    for (int mode = 0; mode < 32; ++mode) {
+        double best = 1e30; Result h{};
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaError_t e = launch(mode, 1200, d, smem);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("mode %d failed: %s\n", mode, cudaGetErrorString(e)); return 1; }
+            cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+            best = std::min(best, (double)h.cycles / h.rows);
+        }
+        printf("mode %2d [%s N=%d %s %s %s]: %8.1f clk/row = %6.1f clk/MMA   sample %.0f\n", mode, (mode & 1) ? "pair M=256" : "solo M=128",
+               (mode & 2) ? 256 : 192, (mode & 4) ? "alignedA" : "shiftedA", (mode & 8) ? "commits" : "       ", (mode & 16) ? "2banks" : "      ", best, best / 12, h.sample[0]);
+    }
+    return 0;
+}
