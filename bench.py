@@ -300,7 +300,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * out_bytes, "api": "reve_submit/reve_wait, pinned host buffers",
                     "host_checksum": checksum},
             "gpu_launches": launches,
-            "roofline": {"kernel": "conv3x3_umma_kernel<64,false> (64->64 3x3 + PReLU, tcgen05)",
+            "roofline": {"kernel": "conv3x3_umma_kernel<64,false,false> (64->64 3x3 + PReLU, tcgen05, rotating TMEM banks)",
                          "bound": "tensor", "achieved": body_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": body_tflops / peak,
                          "traffic": (lambda t: None if not t else t["dram_bytes_per_launch"] * frames_per_launch / t["frames_per_launch"])(measured_traffic()),

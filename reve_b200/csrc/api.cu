@@ -387,6 +387,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     }
     // REVE_DEBUG_FLAGS bit0 (experiments): never sweep in reverse; bit1: CTA pairs; bit2: swap the pair's B halves.
     ctx->pair = (dflags & 2u) != 0;
+    if (const char* pe = std::getenv("REVE_CTA_PAIRS")) ctx->pair = std::atoi(pe) != 0;   // measured: same frames/s (power-bound), see profiles/r01_notes.md
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         p = ConvParams{};

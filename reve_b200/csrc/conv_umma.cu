@@ -208,7 +208,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         reinterpret_cast<float*>(base_ptr + kOffSlope)[threadIdx.x - 64] = p.slope[threadIdx.x - 64];
     }
     tc_fence_before();
-    __syncthreads();
+    // pair: the barriers must be initialised (and the pair-wide TMEM allocation complete) in both CTAs before
+    // either sends the other anything
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kTmemPtr);
 

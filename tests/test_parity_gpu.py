@@ -47,17 +47,22 @@ def test_golden_vectors(path):
     check(out, g["out"])
 
 
-@pytest.mark.parametrize("w,h,scale,tile,grid", [
-    (100, 30, 2, 0, "1"),      # one CTA walks the whole strip: full 3-slot window, ring wrap
-    (300, 40, 2, 0, "2"),      # CTAs spanning two strips
-    (300, 200, 2, 0, None),    # 148 CTAs, 4-5 rows each
-    (200, 150, 2, 64, None),   # several tiles: gap rows/columns, reflect at every border
-    (137, 91, 3, 50, None),    # ragged sizes, x3 (N padded to 32)
-    (150, 90, 4, 0, "3"),      # x4 (N = 48)
+@pytest.mark.parametrize("w,h,scale,tile,grid,pairs", [
+    (100, 30, 2, 0, "1", False),      # one CTA, two streams walking the whole strip: every bank rotation, many ring laps
+    (300, 40, 2, 0, "2", False),      # streams spanning two strips (several segments per stream)
+    (300, 200, 2, 0, None, False),    # 148 CTAs, 2-3 rows per stream
+    (200, 150, 2, 64, None, False),   # several tiles: gap rows/columns, reflect at every border
+    (137, 91, 3, 50, None, False),    # ragged sizes, x3 (N padded to 32)
+    (150, 90, 4, 0, "3", False),      # x4 (N = 48)
+    (300, 40, 2, 0, "2", True),       # one CTA pair (tcgen05 cta_group::2), 4 lock-step streams over 3 strips
+    (200, 150, 2, 64, None, True),    # 74 pairs, tiles
+    (500, 300, 2, 200, "6", True),    # 3 pairs, streams of unequal segment counts (padding steps)
 ])
-def test_per_layer_features_and_output(w, h, scale, tile, grid, monkeypatch):
+def test_per_layer_features_and_output(w, h, scale, tile, grid, pairs, monkeypatch):
     if grid:
         monkeypatch.setenv("REVE_DEBUG_GRID", grid)
+    if pairs:
+        monkeypatch.setenv("REVE_CTA_PAIRS", "1")
     wts = srvgg.make_weights(scale, 1234)
     frame = srvgg.synthetic_frame(w, h, 5, "random")
     model = reve_b200.Model.random(scale, 1234)
