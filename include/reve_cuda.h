@@ -66,6 +66,14 @@ int reve_model_load_ncnn(const char* param_path, const char* bin_path, reve_mode
 /* Seeded He-normal random init of the named architecture (used when the weight files are
  * absent offline).  Bit-identical to oracle/srvgg.py:make_weights(scale, seed). */
 int reve_model_random(int scale, uint64_t seed, reve_model** out);
+/* Build the model from host arrays, e.g. the tensors of a Real-ESRGAN `.pth` checkpoint
+ * (SRVGGNetCompact: `body.{0,2,..,34}.weight/.bias` are the 18 convolutions, `body.{1,3,..,33}.weight`
+ * the 17 PReLU slopes).  conv_w[k]: fp32 OIHW [out_k][in_k][3][3] with
+ * in_0 = 3, out_17 = 3*scale*scale, 64 otherwise; conv_b[k]: [out_k]; prelu[k]: [64] for k < 17
+ * (prelu[17] is ignored).  The arrays are copied.  Weights are stored as given; the device packs them to
+ * fp16 exactly like an fp32 .bin (REVE_E_MODEL if a weight is NaN or outside the fp16 range). */
+int reve_model_from_arrays(int scale, const float* const* conv_w, const float* const* conv_b,
+                           const float* const* prelu, reve_model** out);
 /* Write the model as ncnn .param/.bin (fp16 != 0: tag 0x01306B47 payload). */
 int reve_model_save_ncnn(const reve_model* m, const char* param_path, const char* bin_path, int fp16);
 int reve_model_info(const reve_model* m, int* scale, int* num_feat, int* num_conv);
@@ -124,8 +132,9 @@ int reve_ctx_get_profile(reve_ctx* ctx, reve_profile* out, int reset);
 int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, int layer,
                         float* out, size_t cap_floats, int* canvas_w, int* canvas_h);
 /* Test hook: with REVE_DEBUG_TRACE=1 in the environment at context creation, CTA 0 of body layer 5
- * records clock64() timestamps (MMA warp: out[4*i + 0..2] for input row i; epilogue group leaders:
- * out[1024 + 4*t + 0..2] for output row t); this copies the first n (<= 2048) words out. */
+ * records clock64() timestamps (MMA warp: out[i] at the start of step i, out[1000] = look-ahead misses;
+ * epilogue group 0: out[1024 + 4*e + 0..3] = wait start / accumulator full / slot released / row stored of
+ * event e); this copies the first n (<= 2048) words out.  See tools/gpu_trace.py. */
 int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n);
 /* Canvas geometry tables (context-free, host only; test hook): the canvas is the side-by-side
  * layout of upstream's padded tiles.  For canvas column/row i: the source frame coordinate feeding

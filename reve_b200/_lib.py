@@ -23,6 +23,8 @@ SIGNATURES = {
     "reve_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "reve_model_load_ncnn": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "reve_model_random": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "reve_model_from_arrays": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p)]),
     "reve_model_save_ncnn": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]),
     "reve_model_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "reve_model_free": (None, [C.c_void_p]),

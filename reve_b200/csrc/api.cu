@@ -517,6 +517,28 @@ int reve_model_random(int scale, uint64_t seed, reve_model** out) {
     return REVE_OK;
 }
 
+int reve_model_from_arrays(int scale, const float* const* conv_w, const float* const* conv_b,
+                           const float* const* prelu, reve_model** out) {
+    if (!out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
+    *out = nullptr;
+    reve_model* m = new (std::nothrow) reve_model();
+    if (!m) return set_err(nullptr, REVE_E_NOMEM, "out of host memory");
+    std::string err;
+    int rc;
+    try {
+        rc = model_from_arrays(scale, conv_w, conv_b, prelu, m->m, err);
+    } catch (const std::exception& e) {
+        rc = REVE_E_NOMEM;
+        err = e.what();
+    }
+    if (rc != REVE_OK) {
+        delete m;
+        return set_err(nullptr, rc, err);
+    }
+    *out = m;
+    return REVE_OK;
+}
+
 int reve_model_save_ncnn(const reve_model* m, const char* param_path, const char* bin_path, int fp16) {
     if (!m || !param_path || !bin_path) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
     std::string err;

@@ -346,4 +346,26 @@ int model_save_ncnn(const Model& m, const std::string& param_path, const std::st
     return REVE_OK;
 }
 
+int model_from_arrays(int scale, const float* const* conv_w, const float* const* conv_b, const float* const* prelu,
+                      Model& m, std::string& err) {
+    if (scale < 2 || scale > 4) return fail(err, REVE_E_INVAL, "scale must be 2, 3 or 4");
+    if (!conv_w || !conv_b || !prelu) return fail(err, REVE_E_INVAL, "NULL array table");
+    m.scale = scale;
+    for (int k = 0; k < kNumConv; ++k) {
+        ConvLayer& C = m.conv[k];
+        C.in_ch = (k == 0) ? 3 : kNumFeat;
+        C.out_ch = (k == kNumConv - 1) ? 3 * scale * scale : kNumFeat;
+        if (!conv_w[k] || !conv_b[k] || (k < kNumConv - 1 && !prelu[k]))
+            return fail(err, REVE_E_INVAL, "NULL tensor for convolution " + std::to_string(k));
+        const size_t nw = static_cast<size_t>(C.out_ch) * C.in_ch * 9;
+        C.w.assign(conv_w[k], conv_w[k] + nw);
+        C.b.assign(conv_b[k], conv_b[k] + C.out_ch);
+        if (k < kNumConv - 1) C.slope.assign(prelu[k], prelu[k] + C.out_ch); else C.slope.clear();
+        for (size_t i = 0; i < nw; ++i)
+            if (!(C.w[i] == C.w[i]) || C.w[i] > 65504.f || C.w[i] < -65504.f)
+                return fail(err, REVE_E_MODEL, "weight of convolution " + std::to_string(k) + " is not representable in fp16");
+    }
+    return REVE_OK;
+}
+
 }  // namespace reve

@@ -32,6 +32,9 @@ float f16_to_f32(uint16_t h);
 int model_load_ncnn(const std::string& param_path, const std::string& bin_path, Model& m, std::string& err);
 int model_save_ncnn(const Model& m, const std::string& param_path, const std::string& bin_path, bool fp16, std::string& err);
 int model_random(int scale, uint64_t seed, Model& m, std::string& err);
+// conv_w[k]: OIHW fp32 of convolution k (18), conv_b[k]: bias, prelu[k]: slopes of the PReLU after convolution k (17)
+int model_from_arrays(int scale, const float* const* conv_w, const float* const* conv_b, const float* const* prelu,
+                      Model& m, std::string& err);
 
 }  // namespace reve
 

@@ -61,6 +61,65 @@ class Model:
         return cls(h)
 
     @classmethod
+    def from_arrays(cls, scale: int, conv_w: Sequence[np.ndarray], conv_b: Sequence[np.ndarray],
+                    prelu: Sequence[np.ndarray]) -> "Model":
+        """18 OIHW conv weights, 18 biases, 17 PReLU slope vectors (fp32; copied by the library)."""
+        if len(conv_w) != 18 or len(conv_b) != 18 or len(prelu) != 17:
+            raise ValueError("SRVGGNetCompact(num_conv=16) has 18 convolutions and 17 PReLUs")
+        shapes = [(64, 3, 3, 3)] + [(64, 64, 3, 3)] * 16 + [(3 * scale * scale, 64, 3, 3)]
+        keep = []
+        for k in range(18):
+            w = np.ascontiguousarray(conv_w[k], np.float32)
+            b = np.ascontiguousarray(conv_b[k], np.float32)
+            if w.shape != shapes[k] or b.shape != (shapes[k][0],):
+                raise ValueError(f"convolution {k}: expected weight {shapes[k]}, got {w.shape} / bias {b.shape}")
+            keep += [w, b]
+        slopes = [np.ascontiguousarray(a, np.float32) for a in prelu]
+        if any(a.shape != (64,) for a in slopes):
+            raise ValueError("PReLU slopes must have shape (64,)")
+        arr = C.c_void_p * 18
+        pw = arr(*[keep[2 * k].ctypes.data for k in range(18)])
+        pb = arr(*[keep[2 * k + 1].ctypes.data for k in range(18)])
+        ps = arr(*([a.ctypes.data for a in slopes] + [None]))
+        h = C.c_void_p()
+        _check(_lib.load().reve_model_from_arrays(scale, pw, pb, ps, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_state_dict(cls, sd, scale: Optional[int] = None) -> "Model":
+        """A Real-ESRGAN SRVGGNetCompact state dict (``body.{0,2,..,34}.weight/.bias`` = convolutions,
+        ``body.{1,3,..,33}.weight`` = PReLU slopes; values: torch tensors or numpy arrays).  Checkpoints
+        wrap it as ``{"params": ...}`` or ``{"params_ema": ...}``; either is unwrapped
+        (SURVEY.md section 8(f) row 4)."""
+        for key in ("params_ema", "params"):
+            if key in sd and hasattr(sd[key], "keys"):
+                sd = sd[key]
+                break
+
+        def arr(name):
+            if name not in sd:
+                raise ValueError(f"state dict has no '{name}': not a realesr-animevideov3 (SRVGGNetCompact num_conv=16) checkpoint")
+            v = sd[name]
+            if hasattr(v, "detach"):
+                v = v.detach().cpu().float().numpy()
+            return np.asarray(v, np.float32)
+
+        conv_w = [arr(f"body.{2 * k}.weight") for k in range(18)]
+        conv_b = [arr(f"body.{2 * k}.bias") for k in range(18)]
+        prelu = [arr(f"body.{2 * k + 1}.weight").reshape(-1) for k in range(17)]
+        out_ch = conv_w[17].shape[0]
+        s = {12: 2, 27: 3, 48: 4}.get(out_ch)
+        if s is None or (scale is not None and scale != s):
+            raise ValueError(f"last convolution has {out_ch} output channels: not a x{scale or '2/3/4'} model")
+        return cls.from_arrays(s, conv_w, conv_b, prelu)
+
+    @classmethod
+    def from_pth(cls, path: str, scale: Optional[int] = None) -> "Model":
+        """``realesr-animevideov3.pth`` and friends (needs torch to unpickle the checkpoint)."""
+        import torch
+        return cls.from_state_dict(torch.load(path, map_location="cpu", weights_only=True), scale)
+
+    @classmethod
     def for_scale(cls, scale: int, model_dir: str = "models", seed: int = 0) -> "Model":
         """The model the reference's CLI intends for ``-s scale``:
         ``<model_dir>/realesr-animevideov3-x{scale}.param|.bin`` if present, otherwise the seeded
@@ -68,6 +127,8 @@ class Model:
         base = os.path.join(model_dir, f"realesr-animevideov3-x{scale}")
         if os.path.exists(base + ".param") and os.path.exists(base + ".bin"):
             return cls.load_ncnn(base + ".param", base + ".bin")
+        if os.path.exists(base + ".pth"):
+            return cls.from_pth(base + ".pth", scale)
         return cls.random(scale, seed)
 
     def save_ncnn(self, param_path: str, bin_path: str, fp16: bool = True) -> None:

@@ -189,3 +189,60 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "srvgg_ref" not in txt, f
+
+
+def _srvgg_state_dict(w):
+    """State dict of Real-ESRGAN's SRVGGNetCompact(num_conv=16) holding the oracle weights `w`: nn.Sequential
+    `body` of conv, PReLU, conv, PReLU, ..., conv (indices 0..34)."""
+    import torch
+    sd = {}
+    for k in range(18):
+        sd[f"body.{2 * k}.weight"] = torch.from_numpy(w.conv_w[k].copy())
+        sd[f"body.{2 * k}.bias"] = torch.from_numpy(w.conv_b[k].copy())
+        if k < 17:
+            sd[f"body.{2 * k + 1}.weight"] = torch.from_numpy(w.slopes[k].copy())
+    return sd
+
+
+@pytest.mark.parametrize("scale", [2, 3, 4])
+def test_pth_ingestion_matches_ncnn_route(lib, tmp_path, scale):
+    """a .pth checkpoint (params / params_ema wrapper) gives the same model as
+    the .param/.bin pair of the same weights."""
+    import torch
+    w = srvgg.make_weights(scale, 11)
+    pth = str(tmp_path / "realesr-animevideov3.pth")
+    torch.save({"params_ema": _srvgg_state_dict(w)}, pth)
+    m = reve_b200.Model.from_pth(pth)
+    assert m.scale == scale
+    p, b = str(tmp_path / "m.param"), str(tmp_path / "m.bin")
+    m.save_ncnn(p, b, fp16=False)
+    got = srvgg.read_ncnn(p, b)
+    assert all(np.array_equal(x, y) for x, y in zip(got.conv_w, w.conv_w))
+    assert all(np.array_equal(x, y) for x, y in zip(got.conv_b, w.conv_b))
+    assert all(np.array_equal(x, y) for x, y in zip(got.slopes, w.slopes))
+    # for_scale picks the checkpoint up from a models directory
+    os.makedirs(tmp_path / "models")
+    torch.save({"params": _srvgg_state_dict(w)}, str(tmp_path / "models" / f"realesr-animevideov3-x{scale}.pth"))
+    m2 = reve_b200.Model.for_scale(scale, str(tmp_path / "models"))
+    m2.save_ncnn(p, b, fp16=False)
+    assert all(np.array_equal(x, y) for x, y in zip(srvgg.read_ncnn(p, b).conv_w, w.conv_w))
+
+
+def test_pth_ingestion_rejects_foreign_checkpoints(lib):
+    w = srvgg.make_weights(2, 3)
+    sd = _srvgg_state_dict(w)
+    with pytest.raises(ValueError):
+        reve_b200.Model.from_state_dict({k: v for k, v in sd.items() if not k.startswith("body.34")})
+    with pytest.raises(ValueError):
+        reve_b200.Model.from_state_dict(sd, scale=3)              # a x2 checkpoint asked for as x3
+    bad = dict(sd)
+    bad["body.4.weight"] = sd["body.4.weight"][:, :32]
+    with pytest.raises(ValueError):
+        reve_b200.Model.from_state_dict(bad)
+    nan = dict(sd)
+    t = sd["body.6.weight"].clone()
+    t[0, 0, 0, 0] = float("nan")
+    nan["body.6.weight"] = t
+    with pytest.raises(reve_b200.ReveError) as e:
+        reve_b200.Model.from_state_dict(nan)
+    assert e.value.status == -5
