@@ -89,6 +89,24 @@ void reve_ctx_destroy(reve_ctx* ctx);
 /* Geometry of the context: output frame size and scale. */
 int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale);
 
+/* Output pixel format.  The reference pipes the upscaled PNGs into
+ * `ffmpeg ... -pix_fmt yuv420p10le -c:v libx265` (reve-cli/src/main.rs:306-326), so swscale converts every
+ * frame on the host; with a YUV format the frames leave the GPU in the encoder's native layout instead
+ * (same 3 bytes per pixel over PCIe), ready for `ffmpeg -f rawvideo -pix_fmt yuv420p10le -s WxH -i pipe:0`.
+ * Planar, 16-bit little-endian samples holding 10 bits, limited range (Y 64..940, C 64..960), 2x2 box-filtered
+ * chroma, integer arithmetic defined in reve_b200/csrc/yuv.cu (restated in oracle/colour.py).  BT601 is what
+ * swscale applies to untagged RGB input (the reference's behaviour); BT709 is the HD matrix.
+ * Buffer layout for reve_submit / reve_upscale_device: Y plane (out_h rows of out_stride bytes), then the U
+ * plane and the V plane (ceil(out_h/2) rows of out_stride/2 bytes each).  Not while frames are in flight. */
+typedef enum reve_format {
+    REVE_FMT_RGB24 = 0,
+    REVE_FMT_YUV420P10LE_BT601 = 1,
+    REVE_FMT_YUV420P10LE_BT709 = 2
+} reve_format;
+int reve_ctx_set_output_format(reve_ctx* ctx, int format);
+/* Smallest legal out_stride for the current format and the bytes of one frame stored with it. */
+int reve_ctx_output_layout(const reve_ctx* ctx, size_t* min_stride, size_t* frame_bytes);
+
 /* Pinned host memory for frame buffers (plain malloc'ed buffers work too, but copy slower and
  * do not overlap). */
 int reve_host_alloc(size_t bytes, void** out);
@@ -106,7 +124,8 @@ int reve_wait(reve_ctx* ctx, uint64_t* tag);
 int reve_sync(reve_ctx* ctx);
 
 /* Device-resident variant (kernel-only benchmarks, or callers that already hold frames on the
- * GPU): d_in = n_frames packed frames (3*in_w*in_h bytes each), d_out likewise at output size.
+ * GPU): d_in = n_frames packed frames (3*in_w*in_h bytes each), d_out likewise at output size (YUV formats:
+ * frames of reve_ctx_output_layout's frame_bytes with the minimal stride).
  * Enqueued on the context's compute stream; returns without synchronising. */
 int reve_upscale_device(reve_ctx* ctx, const void* d_in, void* d_out, int n_frames);
 /* The context's compute stream (a cudaStream_t), for callers that time with their own events. */
@@ -120,6 +139,7 @@ typedef struct reve_profile {
     uint64_t timed_frames;             /* tail launches (= batches) covered by the timings */
     uint64_t frames;                   /* frames enqueued since reset */
     uint64_t body_frames;              /* sum over body launches of the frames each one processed */
+    uint64_t launches_yuv;             /* colour-conversion kernels (one per frame when the output is YUV) */
 } reve_profile;
 /* on != 0: bracket every kernel launch with CUDA events (slower; for roofline measurements). */
 int reve_ctx_set_profiling(reve_ctx* ctx, int on);

@@ -12,7 +12,7 @@ class reve_profile(C.Structure):
     _fields_ = [("launches_conv0", C.c_uint64), ("launches_body", C.c_uint64),
                 ("launches_tail", C.c_uint64), ("ms_conv0", C.c_double), ("ms_body", C.c_double),
                 ("ms_tail", C.c_double), ("timed_body", C.c_uint64), ("timed_frames", C.c_uint64),
-                ("frames", C.c_uint64), ("body_frames", C.c_uint64)]
+                ("frames", C.c_uint64), ("body_frames", C.c_uint64), ("launches_yuv", C.c_uint64)]
 
 
 # name -> (restype, argtypes); mirrors include/reve_cuda.h one to one
@@ -32,6 +32,8 @@ SIGNATURES = {
                                   C.POINTER(C.c_void_p)]),
     "reve_ctx_destroy": (None, [C.c_void_p]),
     "reve_ctx_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
+    "reve_ctx_set_output_format": (C.c_int, [C.c_void_p, C.c_int]),
+    "reve_ctx_output_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "reve_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "reve_host_free": (None, [C.c_void_p]),
     "reve_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64]),

@@ -64,6 +64,9 @@ struct reve_ctx {
     Conv0Params c0;
     ConvParams body[kNumBody];
     ConvParams tail;
+    int out_format = REVE_FMT_RGB24;
+    YuvCoeffs yuv = {};
+    uint8_t* rgb_scratch[kMaxBatch] = {};   // tail output when the frame leaves as yuv420p10le
     int grid = 0;
     bool pair = false;    // body layers run as CTA pairs (tcgen05 cta_group::2)
     DebugBlock* dbg_host = nullptr;
@@ -125,6 +128,25 @@ int upload(reve_ctx* ctx, T** dptr, const void* src, size_t bytes) {
     return REVE_OK;
 }
 
+struct OutLayout {
+    int w, h, cw, ch;            // output luma size, chroma plane size
+    size_t rgb_row, rgb_bytes;   // packed RGB
+    size_t y_row, c_row, yuv_bytes;   // packed planar yuv420p10le
+};
+OutLayout out_layout(const reve_ctx* ctx) {
+    OutLayout o;
+    o.w = ctx->g.in_w * ctx->scale;
+    o.h = ctx->g.in_h * ctx->scale;
+    o.cw = (o.w + 1) / 2;
+    o.ch = (o.h + 1) / 2;
+    o.rgb_row = static_cast<size_t>(o.w) * 3;
+    o.rgb_bytes = o.rgb_row * o.h;
+    o.c_row = static_cast<size_t>(o.cw) * 2;
+    o.y_row = o.c_row * 2;       // >= 2*w and a multiple of 4: the chroma pitch is half the luma pitch
+    o.yuv_bytes = o.y_row * o.h + 2 * o.c_row * o.ch;
+    return o;
+}
+
 void prof_mark(reve_ctx* ctx, int kind) {
     if (!ctx->profiling) return;
     cudaEvent_t ev;
@@ -164,15 +186,29 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
         ConvParams t = ctx->tail;
         t.canvas_h = ch;
         t.total_rows = static_cast<int>(total);
+        const bool yuv = ctx->out_format != REVE_FMT_RGB24;
         for (int f = 0; f < n; ++f) {
             t.src[f] = d_in[f];
-            t.dst[f] = d_out[f];
+            t.dst[f] = yuv ? ctx->rgb_scratch[f] : d_out[f];
         }
         t.src_stride = in_stride;
         t.dst_stride = out_stride;
         CK(ctx, launch_conv_tail(ctx->s_comp, grid, ctx->scale, ctx->map_in[0], t));
         ctx->prof.launches_tail++;
         prof_mark(ctx, 2);
+        if (yuv) {   // d_out[f] receives the packed planar frame: Y, then U, then V
+            const OutLayout o = out_layout(ctx);
+            for (int f = 0; f < n; ++f) {
+                uint8_t* const y = d_out[f];
+                uint8_t* const u = y + o.y_row * o.h;
+                uint8_t* const v = u + o.c_row * o.ch;
+                CK(ctx, launch_rgb_to_yuv420p10(ctx->s_comp, ctx->rgb_scratch[f], out_stride, o.w, o.h,
+                                                reinterpret_cast<uint16_t*>(y), static_cast<long long>(o.y_row),
+                                                reinterpret_cast<uint16_t*>(u), reinterpret_cast<uint16_t*>(v),
+                                                static_cast<long long>(o.c_row), ctx->yuv));
+                ctx->prof.launches_yuv++;
+            }
+        }
     }
     ctx->prof.frames += n;
     return REVE_OK;
@@ -196,9 +232,21 @@ int flush_pending(reve_ctx* ctx) {
     const int out_h = ctx->g.in_h * ctx->scale;
     CK(ctx, cudaEventRecord(ctx->ring[ctx->pending[0]].ev_comp, ctx->s_comp));
     CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ring[ctx->pending[0]].ev_comp, 0));
+    const OutLayout o = out_layout(ctx);
     for (int f = 0; f < n; ++f) {
         Slot& s = ctx->ring[ctx->pending[f]];
-        CK(ctx, cudaMemcpy2DAsync(s.host_out, s.host_out_stride, s.d_out, out_row, out_row, out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (ctx->out_format == REVE_FMT_RGB24) {
+            CK(ctx, cudaMemcpy2DAsync(s.host_out, s.host_out_stride, s.d_out, out_row, out_row, out_h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        } else {   // three planes; the host chroma pitch is half the host luma pitch
+            const size_t hs = s.host_out_stride, hc = hs / 2;
+            uint8_t* const hu = s.host_out + hs * o.h;
+            uint8_t* const hv = hu + hc * o.ch;
+            const uint8_t* const du = s.d_out + o.y_row * o.h;
+            const uint8_t* const dv = du + o.c_row * o.ch;
+            CK(ctx, cudaMemcpy2DAsync(s.host_out, hs, s.d_out, o.y_row, static_cast<size_t>(o.w) * 2, o.h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaMemcpy2DAsync(hu, hc, du, o.c_row, o.c_row, o.ch, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaMemcpy2DAsync(hv, hc, dv, o.c_row, o.c_row, o.ch, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
         CK(ctx, cudaEventRecord(s.ev_done, ctx->s_d2h));
     }
     ctx->pending.clear();
@@ -247,6 +295,7 @@ void destroy_ctx(reve_ctx* ctx) {
     for (void* p : ctx->d_wblob) cudaFree(p);
     cudaFree(ctx->d_w0);
     cudaFree(ctx->d_trace);
+    for (uint8_t* p : ctx->rgb_scratch) cudaFree(p);
     if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -427,7 +476,8 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     // staging ring
     ctx->ring.resize(ring_depth);
     const size_t in_bytes = static_cast<size_t>(in_w) * in_h * 3;
-    const size_t out_bytes = in_bytes * m.scale * m.scale;
+    const OutLayout ol = out_layout(ctx);
+    const size_t out_bytes = ol.rgb_bytes > ol.yuv_bytes ? ol.rgb_bytes : ol.yuv_bytes;   // either output format
     for (auto& s : ctx->ring) {
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&s.d_in), in_bytes));
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&s.d_out), out_bytes));
@@ -614,8 +664,11 @@ int reve_submit(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, uint8_t*
                 uint64_t tag) {
     if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
     if (!rgb_in || !rgb_out) return set_err(ctx, REVE_E_INVAL, "frame pointer is NULL");
-    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3, out_row = in_row * ctx->scale;
+    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3;
+    const bool yuv = ctx->out_format != REVE_FMT_RGB24;
+    const size_t out_row = yuv ? out_layout(ctx).y_row : in_row * ctx->scale;
     if (in_stride < in_row || out_stride < out_row) return set_err(ctx, REVE_E_INVAL, "row stride smaller than the row");
+    if (yuv && (out_stride % 4) != 0) return set_err(ctx, REVE_E_INVAL, "yuv420p10le: the luma row stride must be a multiple of 4 bytes");
     if (ctx->inflight == static_cast<int>(ctx->ring.size())) return set_err(ctx, REVE_E_BUSY, "submit ring full: call reve_wait");
     CK(ctx, cudaSetDevice(ctx->device));
     Slot& s = ctx->ring[ctx->head];
@@ -668,7 +721,8 @@ int reve_upscale_device(reve_ctx* ctx, const void* d_in, void* d_out, int n_fram
     if (!d_in || !d_out || n_frames < 0) return set_err(ctx, REVE_E_INVAL, "bad argument");
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3, out_row = in_row * ctx->scale;
-    const size_t in_bytes = in_row * ctx->g.in_h, out_bytes = out_row * ctx->g.in_h * ctx->scale;
+    const size_t in_bytes = in_row * ctx->g.in_h;
+    const size_t out_bytes = ctx->out_format == REVE_FMT_RGB24 ? out_layout(ctx).rgb_bytes : out_layout(ctx).yuv_bytes;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->batch) {
         const int n = (n_frames - f0 < ctx->batch) ? n_frames - f0 : ctx->batch;
         const uint8_t* ins[kMaxBatch];
@@ -680,6 +734,34 @@ int reve_upscale_device(reve_ctx* ctx, const void* d_in, void* d_out, int n_fram
         int rc = enqueue_batch(ctx, n, ins, static_cast<long long>(in_row), outs, static_cast<long long>(out_row));
         if (rc != REVE_OK) return rc;
     }
+    return REVE_OK;
+}
+
+int reve_ctx_set_output_format(reve_ctx* ctx, int format) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    if (format != REVE_FMT_RGB24 && format != REVE_FMT_YUV420P10LE_BT601 && format != REVE_FMT_YUV420P10LE_BT709)
+        return set_err(ctx, REVE_E_INVAL, "unknown output format");
+    if (ctx->inflight) return set_err(ctx, REVE_E_BUSY, "frames in flight");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (format != REVE_FMT_RGB24 && !ctx->rgb_scratch[0]) {
+        const size_t bytes = out_layout(ctx).rgb_bytes;
+        for (int f = 0; f < ctx->batch; ++f) {
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->rgb_scratch[f]), bytes);
+            if (e == cudaErrorMemoryAllocation) return set_err(ctx, REVE_E_NOMEM, "out of device memory for the RGB scratch frames");
+            CK(ctx, e);
+        }
+    }
+    ctx->yuv = colour_coeffs(format == REVE_FMT_YUV420P10LE_BT709 ? 709 : 601);
+    ctx->out_format = format;
+    return REVE_OK;
+}
+
+int reve_ctx_output_layout(const reve_ctx* ctx, size_t* min_stride, size_t* frame_bytes) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    const OutLayout o = out_layout(ctx);
+    const bool yuv = ctx->out_format != REVE_FMT_RGB24;
+    if (min_stride) *min_stride = yuv ? o.y_row : o.rgb_row;
+    if (frame_bytes) *frame_bytes = yuv ? o.yuv_bytes : o.rgb_bytes;
     return REVE_OK;
 }
 

@@ -66,6 +66,15 @@ cudaError_t conv_kernels_init();  // opt-in shared memory attributes; call once 
 // `pair`: launch as clusters of two CTAs driving tcgen05.mma.cta_group::2 (grid rounded down to even)
 cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p);
+// 8-bit RGB -> yuv420p10le (yuv.cu).  Integer coefficients scaled by 2^16; matrix = 601 or 709.
+struct YuvCoeffs {
+    int y[3], u[3], v[3];
+};
+YuvCoeffs colour_coeffs(int matrix);
+// strides in bytes; chroma planes are ceil(w/2) x ceil(h/2)
+cudaError_t launch_rgb_to_yuv420p10(cudaStream_t st, const uint8_t* rgb, long long rgb_stride, int w, int h,
+                                    uint16_t* y, long long y_stride, uint16_t* u, uint16_t* v, long long c_stride,
+                                    const YuvCoeffs& c);
 size_t conv0_weight_blob_bytes();
 void pack_conv0_weights(const float* w_oihw, uint16_t* blob);
 cudaError_t conv0_kernel_init();

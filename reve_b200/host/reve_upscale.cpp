@@ -39,6 +39,7 @@ struct Options {
     std::vector<int> gpus;
     bool verbose = false;
     uint64_t seed = 1234;  // random-init fallback when the weight files are absent offline
+    int out_format = REVE_FMT_RGB24;   // --pix-fmt (raw mode): rgb24 | yuv420p10le (BT.601, as swscale) | yuv420p10le-bt709
     int raw_w = 0, raw_h = 0;  // --raw WxH: rgb24 rawvideo frames on -i (file or "-" = stdin) -> -o (file or "-" = stdout)
 };
 
@@ -55,7 +56,10 @@ int usage() {
                  "usage: reve-upscale -i in_dir -o out_dir [-s 2|3|4] [-n model-name] [-m model-dir] [-t tile]\n"
                  "                    [-g gpu,gpu,...] [-f png] [-v]\n"
                  "       reve-upscale --raw WxH -i in.rgb|- -o out.rgb|- [-s 2|3|4] [-m model-dir] [-t tile] [-g gpu] [-v]\n"
-                 "         (rgb24 rawvideo stream, e.g. ffmpeg -f rawvideo -pix_fmt rgb24 pipes: no PNG on the path)\n");
+                 "                    [--pix-fmt rgb24|yuv420p10le|yuv420p10le-bt709]\n"
+                 "         (rgb24 rawvideo stream in, e.g. ffmpeg -f rawvideo -pix_fmt rgb24 pipes: no PNG on the path;\n"
+                 "          with --pix-fmt yuv420p10le the output is what `ffmpeg -f rawvideo -pix_fmt yuv420p10le\n"
+                 "          -s WxH -i pipe:0 -c:v libx265` ingests without a swscale pass)\n");
     return 2;
 }
 
@@ -221,7 +225,16 @@ int run_raw(const Options& o, const reve_model* model) {
         std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr));
         return 1;
     }
-    const size_t in_bytes = size_t(w) * h * 3, out_bytes = in_bytes * o.scale * o.scale;
+    size_t out_stride = 0, out_bytes = 0;
+    if (reve_ctx_set_output_format(ctx, o.out_format) != REVE_OK || reve_ctx_output_layout(ctx, &out_stride, &out_bytes) != REVE_OK) {
+        std::fprintf(stderr, "error: %s\n", reve_last_error(ctx));
+        return 1;
+    }
+    if (o.out_format != REVE_FMT_RGB24 && ((w * o.scale) % 2 || (h * o.scale) % 2)) {
+        std::fprintf(stderr, "error: yuv420p10le needs an even output size\n");   // rawvideo has no row padding
+        return 1;
+    }
+    const size_t in_bytes = size_t(w) * h * 3;
     std::vector<uint8_t*> hin(depth, nullptr), hout(depth, nullptr);
     for (int i = 0; i < depth; ++i)
         if (reve_host_alloc(in_bytes, reinterpret_cast<void**>(&hin[i])) != REVE_OK ||
@@ -245,7 +258,7 @@ int run_raw(const Options& o, const reve_model* model) {
         const size_t got = std::fread(hin[slot], 1, in_bytes, fin);
         if (got == 0) break;                       // end of stream
         if (got != in_bytes) { std::fprintf(stderr, "error: truncated frame %llu\n", (unsigned long long)submitted); rc = 1; break; }
-        if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], size_t(w) * o.scale * 3, submitted) != REVE_OK) {
+        if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], out_stride, submitted) != REVE_OK) {
             std::fprintf(stderr, "error: %s\n", reve_last_error(ctx));
             rc = 1;
             break;
@@ -285,6 +298,14 @@ int main(int argc, char** argv) {
             const char* v = (i + 1 < argc) ? argv[++i] : nullptr;
             if (!v || std::sscanf(v, "%dx%d", &o.raw_w, &o.raw_h) != 2 || o.raw_w < 1 || o.raw_h < 1) return usage();
         }
+        else if (a == "--pix-fmt") {
+            const char* v = (i + 1 < argc) ? argv[++i] : nullptr;
+            const std::string f = v ? v : "";
+            if (f == "rgb24") o.out_format = REVE_FMT_RGB24;
+            else if (f == "yuv420p10le" || f == "yuv420p10le-bt601") o.out_format = REVE_FMT_YUV420P10LE_BT601;
+            else if (f == "yuv420p10le-bt709") o.out_format = REVE_FMT_YUV420P10LE_BT709;
+            else return usage();
+        }
         else if (a == "-x") { std::fprintf(stderr, "error: TTA (-x) is not supported\n"); return 2; }
         else if (a == "-i" || a == "-o" || a == "-s" || a == "-n" || a == "-m" || a == "-t" || a == "-g" || a == "-f" || a == "-j") {
             const char* v = next();
@@ -300,6 +321,7 @@ int main(int argc, char** argv) {
     if (o.in.empty() || o.out.empty()) return usage();
     if (o.scale < 2 || o.scale > 4) { std::fprintf(stderr, "error: scale must be 2, 3 or 4\n"); return 2; }
     if (o.fmt != "png") { std::fprintf(stderr, "error: only -f png is supported\n"); return 2; }
+    if (o.out_format != REVE_FMT_RGB24 && o.raw_w == 0) { std::fprintf(stderr, "error: --pix-fmt needs --raw (PNG files hold RGB)\n"); return 2; }
     if (o.tile < 0) o.tile = 200;
 
     std::vector<std::string> names;

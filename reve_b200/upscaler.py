@@ -17,6 +17,7 @@ import numpy as np
 from . import _lib
 
 REVE_E_BUSY = -7
+FMT_RGB24, FMT_YUV420P10LE_BT601, FMT_YUV420P10LE_BT709 = 0, 1, 2
 
 
 class ReveError(RuntimeError):
@@ -217,6 +218,39 @@ class Upscaler:
         self.submit(frame, out, 0)
         self.wait()
         return out
+
+    # -- yuv420p10le output (what the reference's x265 encode stage consumes) -----------------------
+    def set_output_format(self, fmt: int) -> None:
+        """FMT_RGB24 (default), FMT_YUV420P10LE_BT601 (swscale's matrix for untagged RGB, i.e. what the
+        reference's `-pix_fmt yuv420p10le` produces) or FMT_YUV420P10LE_BT709."""
+        _check(self._lib.reve_ctx_set_output_format(self._h, fmt), self._h)
+        self.out_format = fmt
+
+    def output_layout(self) -> Tuple[int, int]:
+        """(minimal row stride in bytes, bytes per frame at that stride) for the current format."""
+        a, b = C.c_size_t(), C.c_size_t()
+        _check(self._lib.reve_ctx_output_layout(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
+    def submit_raw(self, frame: np.ndarray, out: np.ndarray, out_stride: int, tag: int = 0) -> None:
+        """`out`: flat u8 buffer laid out as include/reve_cuda.h describes for the current format."""
+        if frame.dtype != np.uint8 or frame.shape != (self.in_h, self.in_w, 3) or frame.strides[1:] != (3, 1):
+            raise ValueError(f"frame must be packed u8 [{self.in_h},{self.in_w},3]")
+        _check(self._lib.reve_submit(self._h, frame.ctypes.data, frame.strides[0], out.ctypes.data, out_stride, tag), self._h)
+
+    def upscale_yuv(self, frame: np.ndarray, out_stride: int = 0):
+        """Synchronous single frame in the current YUV format: (Y [H,W], U [ceil(H/2),ceil(W/2)], V) u16."""
+        stride, _ = self.output_layout()
+        stride = max(stride, out_stride)
+        ch, cw = (self.out_h + 1) // 2, (self.out_w + 1) // 2
+        buf = np.full(stride * self.out_h + 2 * (stride // 2) * ch, 0xAB, np.uint8)
+        self.submit_raw(np.ascontiguousarray(frame), buf, stride, 0)
+        self.wait()
+        y = buf[:stride * self.out_h].reshape(self.out_h, stride)[:, :2 * self.out_w].copy().view("<u2")
+        u = buf[stride * self.out_h:][:(stride // 2) * ch].reshape(ch, stride // 2)
+        v = buf[stride * self.out_h + (stride // 2) * ch:].reshape(ch, stride // 2)
+        self._last_raw = buf
+        return y, u[:, :2 * cw].copy().view("<u2"), v[:, :2 * cw].copy().view("<u2")
 
     def upscale_many(self, frames: Iterable[np.ndarray], outs: Iterable[np.ndarray],
                      on_done: Optional[Callable[[int], None]] = None) -> int:

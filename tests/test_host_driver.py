@@ -90,3 +90,34 @@ def test_raw_rgb24_stream_mode(exe, tmp_path):
     (tmp_path / "bad.rgb").write_bytes(src.read_bytes()[:-5])
     assert subprocess.call([exe, "--raw", f"{w}x{h}", "-i", str(tmp_path / "bad.rgb"), "-o", str(tmp_path / "o.rgb"),
                             "-m", str(tmp_path / "no_models")], stderr=subprocess.DEVNULL) == 1
+
+
+def test_pix_fmt_needs_raw_mode(exe, tmp_path):
+    (tmp_path / "d").mkdir()
+    assert subprocess.call([exe, "-i", str(tmp_path / "d"), "-o", str(tmp_path / "o"), "--pix-fmt", "yuv420p10le"],
+                           stderr=subprocess.DEVNULL) == 2
+    assert subprocess.call([exe, "--raw", "8x8", "-i", "-", "-o", "-", "--pix-fmt", "nv12"], stderr=subprocess.DEVNULL) == 2
+
+
+@pytest.mark.gpu
+def test_raw_stream_yuv420p10le_output(exe, tmp_path):
+    """rgb24 in, planar yuv420p10le out (what `ffmpeg -f rawvideo -pix_fmt yuv420p10le`
+    reads), bit-exact against the colour oracle applied to the RGB stream of the same run."""
+    from oracle import colour
+    w, h, n, s = 160, 90, 5, 2
+    frames = [srvgg.synthetic_frame(w, h, 70 + i, "random" if i % 2 else "edges") for i in range(n)]
+    src, rgb, yuv = tmp_path / "in.rgb", tmp_path / "out.rgb", tmp_path / "out.yuv"
+    src.write_bytes(b"".join(f.tobytes() for f in frames))
+    base = [exe, "--raw", f"{w}x{h}", "-i", str(src), "-s", str(s), "-m", str(tmp_path / "no_models")]
+    assert subprocess.call(base + ["-o", str(rgb)]) == 0
+    assert subprocess.call(base + ["-o", str(yuv), "--pix-fmt", "yuv420p10le"]) == 0
+    W, H = w * s, h * s
+    out_rgb = np.frombuffer(rgb.read_bytes(), np.uint8).reshape(n, H, W, 3)
+    raw = np.frombuffer(yuv.read_bytes(), "<u2")
+    assert raw.size == n * (W * H * 3 // 2)
+    per = raw.reshape(n, W * H * 3 // 2)
+    for i in range(n):
+        y, u, v = colour.rgb_to_yuv420p10(out_rgb[i], 601)
+        assert np.array_equal(per[i, :W * H].reshape(H, W), y)
+        assert np.array_equal(per[i, W * H:W * H * 5 // 4].reshape(H // 2, W // 2), u)
+        assert np.array_equal(per[i, W * H * 5 // 4:].reshape(H // 2, W // 2), v)

@@ -137,3 +137,32 @@ def test_rejects_bad_arguments():
         srvgg.upscale(np.zeros((8, 8), np.uint8), w)
     with pytest.raises(ValueError):
         srvgg.make_weights(5, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# colour conversion oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("matrix", [601, 709])
+def test_yuv_oracle_known_answers_and_float_form(matrix):
+    from oracle import colour
+    # known answers of the limited-range 10-bit encoding: black, white, mid grey carry no chroma
+    for val, y10 in ((0, 64), (255, 940), (128, 504)):
+        f = np.full((4, 4, 3), val, np.uint8)
+        y, u, v = colour.rgb_to_yuv420p10(f, matrix)
+        assert (y == y10).all() and (u == 512).all() and (v == 512).all()
+    # primaries: red drives Cr to its maximum (960), blue drives Cb to its maximum
+    red = np.zeros((2, 2, 3), np.uint8); red[..., 0] = 255
+    blue = np.zeros((2, 2, 3), np.uint8); blue[..., 2] = 255
+    kr, kb = colour.KR_KB[matrix]
+    y, u, v = colour.rgb_to_yuv420p10(red, matrix)
+    assert v[0, 0] == 960 and y[0, 0] == round(64 + 876 * kr)
+    y, u, v = colour.rgb_to_yuv420p10(blue, matrix)
+    assert u[0, 0] == 960 and y[0, 0] == round(64 + 876 * kb)
+    # the integer definition stays within one code value of the fp64 textbook equations (odd sizes too)
+    rng = np.random.default_rng(5)
+    f = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    yi, ui, vi = colour.rgb_to_yuv420p10(f, matrix)
+    yf, uf, vf = colour.rgb_to_yuv420p10_float(f, matrix)
+    assert yi.shape == (37, 53) and ui.shape == (19, 27) and vi.shape == (19, 27)
+    assert np.abs(yi - yf).max() <= 0.51 and np.abs(ui - uf).max() <= 0.51 and np.abs(vi - vf).max() <= 0.51
+    assert yi.min() >= 64 and yi.max() <= 940 and ui.min() >= 64 and ui.max() <= 960

@@ -269,3 +269,66 @@ def test_upscale_segment_directory_contract(tmp_path):
         check(got, srvgg.upscale(f, wts, tile=200, prepad=10))
     with pytest.raises(ValueError):
         reve_b200.upscale_segment(str(indir), str(tmp_path / "o2"), 3, model=model)   # scale / model mismatch
+
+
+@pytest.mark.parametrize("w,h,scale,fmt,matrix", [
+    (96, 64, 2, reve_b200.FMT_YUV420P10LE_BT601, 601),     # aligned fast path
+    (96, 64, 4, reve_b200.FMT_YUV420P10LE_BT709, 709),
+    (137, 91, 3, reve_b200.FMT_YUV420P10LE_BT601, 601),    # odd output size (411 x 273): edge replication, scalar path
+    (51, 33, 2, reve_b200.FMT_YUV420P10LE_BT709, 709),     # even height, width not a multiple of 4
+])
+def test_yuv420p10le_output_is_bit_exact(w, h, scale, fmt, matrix):
+    """the frame leaves the GPU as yuv420p10le; integer work, so bit-exact
+    against oracle/colour.py applied to the RGB output of the same context."""
+    from oracle import colour
+    model = reve_b200.Model.random(scale, 9)
+    frame = srvgg.synthetic_frame(w, h, 4, "edges")
+    frame[::2, ::3] = srvgg.synthetic_frame(w, h, 5, "random")[::2, ::3]
+    with reve_b200.Upscaler(model, w, h, tile=64, prepad=10, ring_depth=4) as up:
+        rgb = up.upscale(frame)
+        up.set_output_format(fmt)
+        stride, nbytes = up.output_layout()
+        cw, ch = (up.out_w + 1) // 2, (up.out_h + 1) // 2
+        assert stride == 4 * cw and nbytes == stride * up.out_h + stride * ch
+        y, u, v = up.upscale_yuv(frame)
+        ry, ru, rv = colour.rgb_to_yuv420p10(rgb, matrix)
+        assert np.array_equal(y, ry) and np.array_equal(u, ru) and np.array_equal(v, rv)
+        # a wider pitch: bytes between the rows are untouched
+        y2, u2, v2 = up.upscale_yuv(frame, out_stride=stride + 64)
+        assert np.array_equal(y2, ry) and np.array_equal(u2, ru) and np.array_equal(v2, rv)
+        raw = up._last_raw
+        rows = raw[:(stride + 64) * up.out_h].reshape(up.out_h, stride + 64)
+        assert (rows[:, stride:] == 0xAB).all()
+        # several frames in flight (one batch), then back to RGB
+        bufs = [np.zeros(nbytes, np.uint8) for _ in range(3)]
+        for i, b in enumerate(bufs):
+            up.submit_raw(frame, b, stride, i)
+        assert [up.wait() for _ in range(3)] == [0, 1, 2]
+        for b in bufs:
+            assert np.array_equal(b[:stride * up.out_h].reshape(up.out_h, stride)[:, :2 * up.out_w].copy().view("<u2"), ry)
+        assert up.profile()["launches_yuv"] >= 5
+        up.set_output_format(reve_b200.FMT_RGB24)
+        assert np.array_equal(up.upscale(frame), rgb)
+
+
+def test_yuv_format_error_paths():
+    model = reve_b200.Model.random(2, 9)
+    with reve_b200.Upscaler(model, 40, 20, ring_depth=2) as up:
+        with pytest.raises(reve_b200.ReveError) as e:
+            up.set_output_format(7)
+        assert e.value.status == -1
+        up.set_output_format(reve_b200.FMT_YUV420P10LE_BT601)
+        stride, nbytes = up.output_layout()
+        buf = np.zeros(nbytes, np.uint8)
+        frame = srvgg.synthetic_frame(40, 20, 1, "random")
+        with pytest.raises(reve_b200.ReveError) as e:
+            up.submit_raw(frame, buf, stride - 4)              # pitch too small
+        assert e.value.status == -1
+        with pytest.raises(reve_b200.ReveError) as e:
+            up.submit_raw(frame, np.zeros(2 * nbytes, np.uint8), stride + 2)   # pitch not a multiple of 4
+        assert e.value.status == -1
+        up.submit_raw(frame, buf, stride, 1)
+        with pytest.raises(reve_b200.ReveError) as e:
+            up.set_output_format(reve_b200.FMT_RGB24)          # frames in flight
+        assert e.value.status == -7
+        assert up.wait() == 1
