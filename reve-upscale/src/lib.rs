@@ -29,6 +29,13 @@ extern "C" {
     fn reve_host_free(p: *mut c_void);
     fn reve_submit(ctx: *mut ReveCtx, rgb_in: *const u8, in_stride: usize, rgb_out: *mut u8, out_stride: usize, tag: u64) -> c_int;
     fn reve_wait(ctx: *mut ReveCtx, tag: *mut u64) -> c_int;
+    #[allow(dead_code)]
+    fn reve_ctx_set_output_format(ctx: *mut ReveCtx, format: c_int) -> c_int;
+    #[allow(dead_code)]
+    fn reve_ctx_output_layout(ctx: *const ReveCtx, min_stride: *mut usize, frame_bytes: *mut usize) -> c_int;
+    #[allow(dead_code)]
+    fn reve_model_from_arrays(scale: c_int, conv_w: *const *const f32, conv_b: *const *const f32,
+                              prelu: *const *const f32, out: *mut *mut ReveModel) -> c_int;
 }
 
 fn last_error(ctx: *const ReveCtx) -> String {
