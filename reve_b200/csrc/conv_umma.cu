@@ -410,6 +410,24 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             }
             const int pr = rev ? CH - 1 - y : y;  // physical canvas row
             const int slot = e % 3;
+            // everything the row needs from global memory is fetched before waiting for its accumulator
+            bool keep = false;
+            int oy = -1, fr = 0;
+            float xin[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+                if constexpr (!TAIL) {
+                    keep = colok && (p.rowflag[pr] != 0);
+                } else {
+                    oy = p.out_y[pr];
+                    if (ox >= 0 && oy >= 0) {
+                        fr = p.row_frame[pr];
+                        const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
+                        xin[0] = static_cast<float>(sp[0]);
+                        xin[1] = static_cast<float>(sp[1]);
+                        xin[2] = static_cast<float>(sp[2]);
+                    }
+                }
+            }
             long long* const tr = (p.trace && blockIdx.x == 0 && grp == 0 && e < 256 && q == 0 && lane == 0)
                                       ? p.trace + 1024 + e * 4 : nullptr;
             if (tr) tr[0] = clock64();
@@ -437,7 +455,6 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             if (!valid) continue;
 
             if constexpr (!TAIL) {
-                const bool keep = colok && (p.rowflag[pr] != 0);
                 const uint32_t stg = base + kOffStage + grp * kRowBytes;
                 const bool gleader = (q == 0 && lane == 0);
                 if (gleader) bulk_wait_read<0>();   // this group's previous row has left the staging buffer
@@ -477,12 +494,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if (tr) tr[3] = clock64();
             } else {
                 constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
-                const int oy = p.out_y[pr];
                 if (ox >= 0 && oy >= 0) {
-                    const int fr = p.row_frame[pr];
-                    const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
-                    const float xin[3] = {static_cast<float>(sp[0]), static_cast<float>(sp[1]),
-                                          static_cast<float>(sp[2])};
                     // S*3 consecutive bytes per output row: packed into 16-/32-bit stores when aligned
                     const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
 #pragma unroll
