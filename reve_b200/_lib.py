@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libreve_cuda.so")
+LIB_PATH = os.environ.get("REVE_LIB") or os.path.join(_HERE, "libreve_cuda.so")   # REVE_LIB: A/B runs against another build
 
 
 class reve_profile(C.Structure):

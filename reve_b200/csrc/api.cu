@@ -53,6 +53,7 @@ struct reve_ctx {
     size_t act_bytes = 0;
     uint8_t *d_colflag = nullptr, *d_rowflag = nullptr;
     int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr, *d_rowframe = nullptr;
+    uint32_t* d_rowpack = nullptr;
     int batch = 1;        // frames stacked on the canvas per launch set (<= kMaxBatch)
     int frame_ch = 0;     // canvas rows of one frame (frames are frame_ch + 1 rows apart: one gap row)
     int n_strips = 0;
@@ -292,6 +293,7 @@ void destroy_ctx(reve_ctx* ctx) {
     cudaFree(ctx->d_outx);
     cudaFree(ctx->d_outy);
     cudaFree(ctx->d_rowframe);
+    cudaFree(ctx->d_rowpack);
     for (void* p : ctx->d_wblob) cudaFree(p);
     cudaFree(ctx->d_w0);
     cudaFree(ctx->d_trace);
@@ -361,6 +363,12 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     if ((rc = upload(ctx, &ctx->d_outx, g.x.out.data(), sizeof(int) * cw))) return rc;
     if ((rc = upload(ctx, &ctx->d_outy, outy.data(), sizeof(int) * ch))) return rc;
     if ((rc = upload(ctx, &ctx->d_rowframe, rowframe.data(), sizeof(int) * ch))) return rc;
+    if (in_h > 32000) return set_err(ctx, REVE_E_INVAL, "frames taller than 32000 rows are not supported");
+    std::vector<uint32_t> rowpack(ch);
+    for (int r = 0; r < ch; ++r)
+        rowpack[r] = (static_cast<uint32_t>(outy[r] + 1) << 17) | (static_cast<uint32_t>(srcy[r] + 1) << 2) |
+                     static_cast<uint32_t>(rowframe[r] < 0 ? 0 : rowframe[r]);
+    if ((rc = upload(ctx, &ctx->d_rowpack, rowpack.data(), sizeof(uint32_t) * ch))) return rc;
 
     // activation canvases (ping-pong), zero-initialised
     ctx->act_bytes = static_cast<size_t>(cw) * ch * 64 * sizeof(__half);
@@ -413,7 +421,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     uint32_t dflags = 0;
     if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) dflags = static_cast<uint32_t>(std::atoi(fe));
     Conv0Params& c0 = ctx->c0;
-    std::memset(&c0, 0, sizeof c0);
+    c0 = Conv0Params{};
     c0.canvas_w = cw;
     c0.canvas_h = ch;
     c0.src_x = ctx->d_srcx;
@@ -425,6 +433,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         c0.bias[co] = m.conv[0].b[co];
         c0.slope[co] = m.conv[0].slope[co];
     }
+    for (int co = 0; co < 64; co += 2) c0.slope2[co >> 1] = __floats2half2_rn(m.conv[0].slope[co], m.conv[0].slope[co + 1]);
     const int n_strips = (cw + kStripPx - 1) / kStripPx;
     ctx->n_strips = n_strips;
     const long long total = static_cast<long long>(n_strips) * ch;
@@ -458,6 +467,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         p.out_x = ctx->d_outx;
         p.out_y = ctx->d_outy;
         p.row_frame = ctx->d_rowframe;
+        p.rowpack = ctx->d_rowpack;
         const ConvLayer& L = m.conv[k + 1];
         for (int c = 0; c < L.out_ch; ++c) {
             p.bias[c] = L.b[c];
@@ -470,7 +480,8 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     if (std::getenv("REVE_DEBUG_TRACE")) {
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_trace), 2048 * sizeof(long long)));
         CK(ctx, cudaMemset(ctx->d_trace, 0, 2048 * sizeof(long long)));
-        ctx->body[5].trace = ctx->d_trace;
+        if (std::string(std::getenv("REVE_DEBUG_TRACE")) == "tail") ctx->tail.trace = ctx->d_trace;
+        else ctx->body[5].trace = ctx->d_trace;
     }
 
     // staging ring

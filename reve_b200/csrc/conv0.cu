@@ -66,13 +66,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
+// Two integers 0..255 as an fp16 pair without the quarter-rate I2F pipe: 0x6400 | v is the fp16 1024 + v
+// (ulp 1 in [1024, 2048)), and subtracting 1024 is exact.
 __device__ __forceinline__ uint32_t pack_u8x2(unsigned a, unsigned b) {
-    const __half2 h = __halves2half2(__ushort2half_rn(static_cast<unsigned short>(a)),
-                                     __ushort2half_rn(static_cast<unsigned short>(b)));
+    const uint32_t biased = 0x64006400u | a | (b << 16);
+    const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&biased), __float2half2_rn(1024.f));
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
@@ -120,8 +118,8 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kTmemPtr);
 
-    const long long npx = static_cast<long long>(CW) * CHh;
-    const int n_tiles = static_cast<int>((npx + 127) / 128);
+    const unsigned npx = static_cast<unsigned>(CW) * static_cast<unsigned>(CHh);   // canvases are far below 2^31 pixels (launch_conv0 checks)
+    const int n_tiles = static_cast<int>((npx + 127u) / 128u);
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------------ im2col producers
@@ -131,12 +129,12 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
             if ((j % kProducerGroups) != static_cast<uint32_t>(pg)) continue;
             const uint32_t stage = j % kStagesA, use = j / kStagesA;
-            const long long px = static_cast<long long>(tile) * 128 + m;
+            const unsigned px = static_cast<unsigned>(tile) * 128u + m;
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = 0u;
             if (px < npx) {
-                const int cy = static_cast<int>(px / CW), cx = static_cast<int>(px - static_cast<long long>(cy) * CW);
+                const int cy = static_cast<int>(px / static_cast<unsigned>(CW)), cx = static_cast<int>(px - static_cast<unsigned>(cy) * CW);
                 if (tx[cx] >= 0 && ty[cy] >= 0) {
                     unsigned v[28];
 #pragma unroll
@@ -214,10 +212,10 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
             if ((j & 1) != static_cast<uint32_t>(grp)) continue;
             const uint32_t buf = j % kAccBufs, ubuf = j / kAccBufs;
-            const long long px = static_cast<long long>(tile) * 128 + m;
+            const unsigned px = static_cast<unsigned>(tile) * 128u + m;
             bool keep = false;
             if (px < npx) {
-                const int cy = static_cast<int>(px / CW), cx = static_cast<int>(px - static_cast<long long>(cy) * CW);
+                const int cy = static_cast<int>(px / static_cast<unsigned>(CW)), cx = static_cast<int>(px - static_cast<unsigned>(cy) * CW);
                 keep = (tx[cx] >= 0) && (ty[cy] >= 0);
             }
             mbar_wait(base + kBarAccFull + 8 * buf, ubuf & 1, dbg, TAG0_ACC_FULL, j);
@@ -244,11 +242,12 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int ch = half * 32 + c8 * 8 + jj * 2;
-                        float v0 = fmaf(__uint_as_float(acc[c8 * 8 + jj * 2]), 1.0f / 255.0f, p.bias[ch]);
-                        float v1 = fmaf(__uint_as_float(acc[c8 * 8 + jj * 2 + 1]), 1.0f / 255.0f, p.bias[ch + 1]);
-                        v0 = fmaxf(v0, 0.f) + p.slope[ch] * fminf(v0, 0.f);
-                        v1 = fmaxf(v1, 0.f) + p.slope[ch + 1] * fminf(v1, 0.f);
-                        pk[jj] = keep ? pack_half2(v0, v1) : 0u;
+                        // acc/255 + bias in fp32, then PReLU on the packed fp16 pair (as in the body kernel)
+                        const __half2 v = __floats2half2_rn(fmaf(__uint_as_float(acc[c8 * 8 + jj * 2]), 1.0f / 255.0f, p.bias[ch]),
+                                                            fmaf(__uint_as_float(acc[c8 * 8 + jj * 2 + 1]), 1.0f / 255.0f, p.bias[ch + 1]));
+                        const __half2 z = __float2half2_rn(0.f);
+                        const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                        pk[jj] = keep ? *reinterpret_cast<const uint32_t*>(&r) : 0u;
                     }
                     st_shared_v4(stg + m * 128 + (((half * 4 + c8) ^ (m & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }

@@ -48,6 +48,7 @@ constexpr int kRowBytes = kBoxPx * 128;  // 16 KB: 128 px * 64 ch * fp16
 constexpr int kCtrlBytes = 2048;
 constexpr int kGuard = 1024;
 constexpr int kMaxStages = 8;
+constexpr int kTailRowTab = 8192;   // canvas rows whose packed geometry the tail keeps in shared memory (32 KB)
 
 __host__ __device__ constexpr int rows_per_dx(int ng, bool pair) { return pair ? 7 * ng / 2 : 5 * ng; }
 __host__ __device__ constexpr int w_smem_bytes(int ng, bool pair) { return 3 * rows_per_dx(ng, pair) * 128; }
@@ -163,6 +164,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     constexpr int kOffW = kCtrlBytes;
     constexpr int kOffRing = kOffW + kWBytes + kGuard;
     constexpr int kOffStage = kOffRing + kStages * kRowBytes + kGuard;  // body: 2 x 16 KB output staging (one per group)
+    constexpr int kOffRowTab = kOffStage;                                // tail: packed row table (kTailRowTab entries)
     static_assert(kWBytes % 1024 == 0, "the A ring must stay 1024-byte aligned");
     static_assert(kStages <= kMaxStages, "ring too deep for the control block");
 
@@ -202,6 +204,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&in_map);
         if (!TAIL) prefetch_tmap(&out_map);
+    }
+    const uint32_t* rowtab = p.rowpack;
+    if constexpr (TAIL) {
+        if (p.canvas_h <= kTailRowTab) {
+            uint32_t* const t = reinterpret_cast<uint32_t*>(base_ptr + kOffRowTab);
+            for (int i = threadIdx.x; i < p.canvas_h; i += kConvThreads) t[i] = p.rowpack[i];
+            rowtab = t;
+        }
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
         reinterpret_cast<float*>(base_ptr + kOffBias)[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
@@ -354,8 +364,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 bool ok = true;
                 if (have) {
                     g = gate_of(i + 1, seq.s, seq.k);
-                    ok = mbar_try_wait(g.bar_f, g.par_f);
-                    if (g.need_e) ok = mbar_try_wait(g.bar_e, g.par_e) && ok;
+                    ok = mbar_test_wait(g.bar_f, g.par_f);   // a poll: must not suspend with 8 MMAs still to issue
+                    if (g.need_e) ok = mbar_test_wait(g.bar_e, g.par_e) && ok;
                 }
                 if (elected) {
 #pragma unroll
@@ -387,47 +397,65 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         stream_range<PAIR>(p, rank, grp, lo, hi);
         Cursor cur(lo, hi, CH);
         const int n_events = U[grp];   // events 0 .. U-1 (event e is completed by step e+1)
-        int x0 = 0, ox = -1, sx = 0;
-        bool colok = false;
-        for (int e = 0; e < n_events; ++e) {
-            bool valid = false;
-            int y = 0;
-            if (e >= 1) {
-                int strip;
-                bool newseg;
-                valid = cur.next(strip, y, newseg);
-                if (newseg) {
-                    x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
-                    const int cx = x0 - 1 + m;
-                    const bool inside = (m >= 1) && (m <= kStripPx) && (cx < p.canvas_w);
-                    colok = inside && (p.colflag[cx] != 0);
-                    ox = -1;
-                    if (TAIL && inside) {
-                        ox = p.out_x[cx];
-                        sx = p.src_x[cx];
-                    }
+        // What an event needs besides its accumulator: the geometry of its canvas row and (tail) the residual
+        // pixel it points to.  Body: one table byte, loaded before the accumulator wait (the group idles ~1000
+        // cycles there anyway).  Tail: its epilogue is the critical resource, so the row table sits in shared
+        // memory (packed, see ConvParams::rowpack) and the residual pixel of event e+1 is prefetched into L1/L2
+        // while event e is processed.  (Carrying in-flight loads across iterations does not work: the compiler
+        // copies their destination registers right after issue, a ~1000-cycle stall per event, measured.)
+        struct Event {
+            bool valid = false, keep = false;
+            int pr = 0, x0 = 0, ox = -1;
+            int oy = -1, fr = 0;             // tail
+            const uint8_t* pix = nullptr;    // tail: residual pixel (3 bytes)
+        };
+        int seg_x0 = 0, seg_ox = -1, seg_sx = 0;
+        bool seg_colok = false;
+        auto make_event = [&](int e) {
+            Event ev;
+            if (e < 1 || e >= n_events) return ev;   // event 0 has no centre step
+            int strip, y;
+            bool newseg;
+            ev.valid = cur.next(strip, y, newseg);
+            if (newseg) {
+                seg_x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
+                const int cx = seg_x0 - 1 + m;
+                const bool inside = (m >= 1) && (m <= kStripPx) && (cx < p.canvas_w);
+                seg_colok = inside && (p.colflag[cx] != 0);
+                seg_ox = -1;
+                if (TAIL && inside) {
+                    seg_ox = p.out_x[cx];
+                    seg_sx = p.src_x[cx];
                 }
             }
-            const int pr = rev ? CH - 1 - y : y;  // physical canvas row
-            const int slot = e % 3;
-            // everything the row needs from global memory is fetched before waiting for its accumulator
-            bool keep = false;
-            int oy = -1, fr = 0;
-            float xin[3] = {0.f, 0.f, 0.f};
-            if (valid) {
+            ev.pr = rev ? CH - 1 - y : y;  // physical canvas row
+            ev.x0 = seg_x0;
+            ev.ox = seg_ox;
+            if (ev.valid) {
                 if constexpr (!TAIL) {
-                    keep = colok && (p.rowflag[pr] != 0);
+                    ev.keep = seg_colok && (p.rowflag[ev.pr] != 0);
                 } else {
-                    oy = p.out_y[pr];
-                    if (ox >= 0 && oy >= 0) {
-                        fr = p.row_frame[pr];
-                        const uint8_t* sp = p.src[fr] + static_cast<long long>(p.src_y[pr]) * p.src_stride + sx * 3;
-                        xin[0] = static_cast<float>(sp[0]);
-                        xin[1] = static_cast<float>(sp[1]);
-                        xin[2] = static_cast<float>(sp[2]);
+                    const uint32_t rp = rowtab[ev.pr];   // (out_y + 1) << 17 | (src_y + 1) << 2 | frame
+                    ev.oy = static_cast<int>(rp >> 17) - 1;
+                    const int sy = static_cast<int>((rp >> 2) & 0x7FFFu) - 1;
+                    ev.fr = static_cast<int>(rp & 3u);
+                    if (ev.ox >= 0 && ev.oy >= 0) {
+                        ev.pix = p.src[ev.fr] + static_cast<long long>(sy) * p.src_stride + seg_sx * 3;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(ev.pix));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(ev.pix + 2));
                     }
                 }
             }
+            return ev;
+        };
+        Event nxt;
+        if constexpr (TAIL) nxt = make_event(0);
+        for (int e = 0; e < n_events; ++e) {
+            Event ev;
+            if constexpr (TAIL) ev = nxt; else ev = make_event(e);
+            const bool valid = ev.valid;
+            const int pr = ev.pr, x0 = ev.x0, ox = ev.ox, oy = ev.oy, fr = ev.fr;
+            const int slot = e % 3;
             long long* const tr = (p.trace && blockIdx.x == 0 && grp == 0 && e < 256 && q == 0 && lane == 0)
                                       ? p.trace + 1024 + e * 4 : nullptr;
             if (tr) tr[0] = clock64();
@@ -452,6 +480,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if constexpr (PAIR) mbar_arrive_cluster(empty_base + 8 * slot); else mbar_arrive(empty_base + 8 * slot);
             }
             if (tr) tr[2] = clock64();
+            if constexpr (TAIL) {
+                // nothing of the next event may be scheduled into the drain above: its cursor depends on `after`
+                int after;
+                asm volatile("mov.u32 %0, 0;" : "=r"(after)::"memory");
+                cur.y += after;
+                nxt = make_event(e + 1);
+                if (tr) tr[3] = clock64();   // tail: next event located (the body records the row store here)
+            }
             if (!valid) continue;
 
             if constexpr (!TAIL) {
@@ -462,7 +498,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if (m >= 1 && m <= kStripPx) {
                     const int row = m - 1;
                     const uint32_t rbase = stg + row * 128;
-                    if (keep) {
+                    if (ev.keep) {
 #pragma unroll
                         for (int c8 = 0; c8 < 8; ++c8) {
                             uint32_t pk[4];
@@ -495,6 +531,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             } else {
                 constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
                 if (ox >= 0 && oy >= 0) {
+                    const unsigned rgb[3] = {ev.pix[0], ev.pix[1], ev.pix[2]};
                     // S*3 consecutive bytes per output row: packed into 16-/32-bit stores when aligned
                     const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
 #pragma unroll
@@ -510,7 +547,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                                 const float v = __uint_as_float(acc[idx]) +
                                                 reinterpret_cast<const float*>(base_ptr + kOffBias)[idx];
                                 // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5))
-                                float o = floorf(fmaf(v, 255.f, xin[c] + 0.5f));
+                                float o = floorf(fmaf(v, 255.f, static_cast<float>(rgb[c]) + 0.5f));
                                 o = fminf(fmaxf(o, 0.f), 255.f);
                                 b[j * 3 + c] = static_cast<uint32_t>(o);
                             }
@@ -547,7 +584,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 template <int NG, bool TAIL, bool PAIR>
 constexpr size_t smem_bytes_t() {
     return 1024 /*alignment slack*/ + kCtrlBytes + w_smem_bytes(NG, PAIR) + kGuard +
-           ring_stages(NG, TAIL, PAIR) * kRowBytes + kGuard + (TAIL ? 0 : 2 * kRowBytes);
+           ring_stages(NG, TAIL, PAIR) * kRowBytes + kGuard + (TAIL ? kTailRowTab * 4 : 2 * kRowBytes);
 }
 
 template <int NG, bool TAIL, bool PAIR>

@@ -32,6 +32,7 @@ struct ConvParams {
     const uint8_t* src[kMaxBatch];  // u8 RGB input frames of the batch (device)
     uint8_t* dst[kMaxBatch];        // u8 RGB output frames (device)
     const int* row_frame;       // [canvas_h] frame of the batch a canvas row belongs to (-1 = gap)
+    const uint32_t* rowpack;    // [canvas_h] the three row tables packed: (out_y + 1) << 17 | (src_y + 1) << 2 | frame
     long long src_stride, dst_stride;
     const int* src_x;           // [canvas_w] source column (or -1)
     const int* src_y;           // [canvas_h]
@@ -55,6 +56,7 @@ struct Conv0Params {
     DebugBlock* dbg;
     float bias[64];
     float slope[64];
+    __half2 slope2[32];        // PReLU slopes as packed fp16 pairs
 };
 
 size_t conv_weight_blob_bytes(int ng);

@@ -45,6 +45,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// Non-blocking poll (try_wait may suspend the thread for a system-dependent time before returning false).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // Bounded wait: a protocol bug must end as a trapped launch with a diagnostic, never as a hung
 // GPU.  ~2^32 cycles (> 2 s at any clock) is far beyond any legitimate wait in these kernels.
 static __device__ __noinline__ void watchdog_fail(DebugBlock* dbg, uint32_t tag, uint32_t a0, uint32_t a1) {

@@ -10,7 +10,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["REVE_DEBUG_TRACE"] = "1"
+os.environ.setdefault("REVE_DEBUG_TRACE", "1")   # "tail": trace the tail kernel instead of body layer 5
 import reve_b200  # noqa: E402
 from reve_b200 import _lib  # noqa: E402
 

@@ -4,6 +4,7 @@
 // descriptors, commits and the B block stride cost?
 //   mode bit0: pair (cta_group::2, M=256)      bit1: N=256 instead of 192      bit2: aligned A only
 //   mode bit3: two multicast commits per row   bit4: alternate two accumulator banks (like two streams)
+//   mode bit5: N=48 (the x2 tail)              bit6: alternate the accumulator per MMA (breaks the dependent chain)
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -35,12 +36,12 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int rows, Result* res)
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(bp + 512);
-    const bool n256 = mode & 2, aligned = mode & 4, commits = mode & 8, banks = mode & 16;
+    const bool n256 = mode & 2, aligned = mode & 4, commits = mode & 8, banks = mode & 16, n48 = mode & 32, alt = mode & 64;
     if (warp == 0 && rank == 0) {
         const uint64_t proto = umma_desc_sw128(0, 0);
         const uint32_t desc_hi = (uint32_t)(proto >> 32), lof = (uint32_t)proto;
         const uint32_t w_lo = lof | (w_addr >> 4), ring_lo = lof | (ring >> 4);
-        const int N = n256 ? 256 : 192;
+        const int N = n48 ? 48 : (n256 ? 256 : 192);
         const uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, N);
         const uint32_t kDx = (PAIR ? N / 2 + 32 : N + 64) * 8;
         long long t0 = clock64();
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int rows, Result* res)
                     const uint64_t ad = mk(desc_hi, a_lo + (aligned ? 0 : (dx - 1) * 8) + k * 2);
                     const uint64_t bd = mk(desc_hi, w_lo + dx * kDx + k * 2);
                     const uint32_t acc = (r > 1 || dxk) ? 1u : 0u;
-                    if constexpr (PAIR) umma_f16_pair(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+                    const uint32_t dd = d + ((alt && (dxk & 1)) ? 64 : 0);
+                    if constexpr (PAIR) umma_f16_pair(dd, ad, bd, idesc, acc); else umma_f16(dd, ad, bd, idesc, acc);
                 }
                 if (commits) {
                     if constexpr (PAIR) { umma_commit_pair(base + 8, 3); umma_commit_pair(base + 16, 3); }
@@ -104,7 +106,8 @@ int main() {
     Result* d; cudaMalloc(&d, sizeof(Result));
     for (int w = 0; w < 50; ++w) launch(0, 1200, d, smem);
     cudaDeviceSynchronize();
-    for (int mode = 0; mode < 32; ++mode) {
+    const int modes[] = {0, 8, 16, 32, 32 + 8, 32 + 16, 32 + 64, 32 + 64 + 8, 32 + 64 + 16, 32 + 4, 32 + 64 + 4};
+    for (int mode : modes) {
         double best = 1e30; Result h{};
         for (int rep = 0; rep < 3; ++rep) {
             cudaError_t e = launch(mode, 1200, d, smem);
@@ -113,8 +116,8 @@ int main() {
             cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
             best = std::min(best, (double)h.cycles / h.rows);
         }
-        printf("mode %2d [%s N=%d %s %s %s]: %8.1f clk/row = %6.1f clk/MMA   sample %.0f\n", mode, (mode & 1) ? "pair M=256" : "solo M=128",
-               (mode & 2) ? 256 : 192, (mode & 4) ? "alignedA" : "shiftedA", (mode & 8) ? "commits" : "       ", (mode & 16) ? "2banks" : "      ", best, best / 12, h.sample[0]);
+        printf("mode %3d [%s N=%d %s %s %s %s]: %8.1f clk/row = %6.1f clk/MMA   sample %.0f\n", mode, (mode & 1) ? "pair M=256" : "solo M=128",
+               (mode & 32) ? 48 : ((mode & 2) ? 256 : 192), (mode & 64) ? "alt-acc" : "chain  ", (mode & 4) ? "alignedA" : "shiftedA", (mode & 8) ? "commits" : "       ", (mode & 16) ? "2banks" : "      ", best, best / 12, h.sample[0]);
     }
     return 0;
 }
