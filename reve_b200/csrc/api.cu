@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,15 @@ struct reve_ctx {
     uint8_t *d_colflag = nullptr, *d_rowflag = nullptr;
     int *d_srcx = nullptr, *d_srcy = nullptr, *d_outx = nullptr, *d_outy = nullptr, *d_rowframe = nullptr;
     uint32_t* d_rowpack = nullptr;
+    // Needed-row lists per margin r (rows within r pixels of a tile's kept region), r < prepad; margins >= prepad
+    // need every row.  One device array per margin: rowmap | run_fwd | run_bwd, each `cap` ints.  rows_n[r][n] =
+    // entries that belong to the first n stacked frames.
+    struct RowMap {
+        int* d = nullptr;
+        int cap = 0;
+        int rows_n[kMaxBatch + 1] = {};
+    };
+    std::vector<RowMap> rowmaps;
     int batch = 1;        // frames stacked on the canvas per launch set (<= kMaxBatch)
     int frame_ch = 0;     // canvas rows of one frame (frames are frame_ch + 1 rows apart: one gap row)
     int n_strips = 0;
@@ -156,13 +166,29 @@ void prof_mark(reve_ctx* ctx, int kind) {
     ctx->prof_events.push_back({kind, ev});
 }
 
+// Rows a layer has to compute when `margin` more convolutions follow it (upstream keeps
+// only the centre of every padded tile, so a row `d` pixels outside the kept region matters only to layers with
+// margin >= d).  n = frames stacked on the canvas, ch = its active rows.
+void set_row_space(const reve_ctx* ctx, ConvParams& p, int margin, int n, int ch) {
+    p.canvas_h = ch;
+    if (margin < static_cast<int>(ctx->rowmaps.size()) && ctx->rowmaps[margin].d) {
+        const reve_ctx::RowMap& rm = ctx->rowmaps[margin];
+        p.n_rows = rm.rows_n[n];
+        p.rowmap = rm.d;
+        p.run_fwd = rm.d + rm.cap;
+        p.run_bwd = rm.d + 2 * rm.cap;
+    } else {
+        p.n_rows = ch;
+        p.rowmap = p.run_fwd = p.run_bwd = nullptr;
+    }
+    p.total_rows = ctx->n_strips * p.n_rows;
+}
+
 // Enqueue the 18 launches of one batch (n <= ctx->batch frames stacked on the canvas, separated by
 // gap rows) on the compute stream.
 int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in_stride, uint8_t* const* d_out,
                   long long out_stride, int stop_after_layers = kNumConv) {
     const int ch = n * (ctx->frame_ch + 1) - 1;   // active canvas rows (the trailing gap row is excluded)
-    const long long total = static_cast<long long>(ctx->n_strips) * ch;
-    const int grid = static_cast<int>(total < ctx->grid ? total : ctx->grid);
     prof_mark(ctx, -1);
     Conv0Params c0 = ctx->c0;
     c0.canvas_h = ch;
@@ -176,8 +202,8 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
     prof_mark(ctx, 0);
     for (int k = 0; k < kNumBody && k + 1 < stop_after_layers; ++k) {
         ConvParams b = ctx->body[k];
-        b.canvas_h = ch;
-        b.total_rows = static_cast<int>(total);
+        set_row_space(ctx, b, kNumBody - k, n, ch);   // body layer k is followed by 16 - k convolutions
+        const int grid = b.total_rows < ctx->grid ? b.total_rows : ctx->grid;
         CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->pair && grid >= 2, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], b));
         ctx->prof.launches_body++;
         ctx->prof.body_frames += n;
@@ -185,8 +211,8 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
     }
     if (stop_after_layers >= kNumConv) {
         ConvParams t = ctx->tail;
-        t.canvas_h = ch;
-        t.total_rows = static_cast<int>(total);
+        set_row_space(ctx, t, 0, n, ch);
+        const int grid = t.total_rows < ctx->grid ? t.total_rows : ctx->grid;
         const bool yuv = ctx->out_format != REVE_FMT_RGB24;
         for (int f = 0; f < n; ++f) {
             t.src[f] = d_in[f];
@@ -294,6 +320,7 @@ void destroy_ctx(reve_ctx* ctx) {
     cudaFree(ctx->d_outy);
     cudaFree(ctx->d_rowframe);
     cudaFree(ctx->d_rowpack);
+    for (auto& rm : ctx->rowmaps) cudaFree(rm.d);
     for (void* p : ctx->d_wblob) cudaFree(p);
     cudaFree(ctx->d_w0);
     cudaFree(ctx->d_trace);
@@ -369,6 +396,44 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         rowpack[r] = (static_cast<uint32_t>(outy[r] + 1) << 17) | (static_cast<uint32_t>(srcy[r] + 1) << 2) |
                      static_cast<uint32_t>(rowframe[r] < 0 ? 0 : rowframe[r]);
     if ((rc = upload(ctx, &ctx->d_rowpack, rowpack.data(), sizeof(uint32_t) * ch))) return rc;
+    // needed-row lists (REVE_DEBUG_FLAGS bit3 disables them: every layer computes every row)
+    {
+        uint32_t df = 0;
+        if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) df = static_cast<uint32_t>(std::atoi(fe));
+        const int n_margins = (df & 8u) ? 0 : prepad;
+        ctx->rowmaps.resize(n_margins);
+        for (int r = 0; r < n_margins; ++r) {
+            std::vector<char> need(ch, 0);
+            for (int b0 = 0; b0 < ch;) {            // bands = maximal runs of tile rows (srcy >= 0)
+                if (srcy[b0] < 0) { ++b0; continue; }
+                int b1 = b0;
+                while (b1 < ch && srcy[b1] >= 0) ++b1;
+                int k0 = b0, k1 = b1;               // kept rows of the band (outy >= 0) are contiguous
+                while (k0 < b1 && outy[k0] < 0) ++k0;
+                while (k1 > k0 && outy[k1 - 1] < 0) --k1;
+                for (int i = std::max(b0, k0 - r); i < std::min(b1, k1 + r); ++i) need[i] = 1;
+                b0 = b1;
+            }
+            std::vector<int> rows;
+            for (int i = 0; i < ch; ++i) if (need[i]) rows.push_back(i);
+            const int cap = static_cast<int>(rows.size());
+            if (cap == 0 || cap == ch) continue;   // nothing to skip: the layer walks the whole canvas
+            std::vector<int> tab(3 * static_cast<size_t>(cap));
+            for (int i = cap - 1; i >= 0; --i)
+                tab[cap + i] = (i + 1 < cap && rows[i + 1] == rows[i] + 1) ? tab[cap + i + 1] + 1 : 1;
+            for (int i = 0; i < cap; ++i) {
+                tab[i] = rows[i];
+                tab[2 * cap + i] = (i > 0 && rows[i - 1] == rows[i] - 1) ? tab[2 * cap + i - 1] + 1 : 1;
+            }
+            reve_ctx::RowMap& rm = ctx->rowmaps[r];
+            rm.cap = cap;
+            for (int nf = 0; nf <= ctx->batch; ++nf) {
+                const int lim = nf * (fch + 1) - 1;   // active canvas rows with nf frames stacked
+                rm.rows_n[nf] = static_cast<int>(std::lower_bound(rows.begin(), rows.end(), lim) - rows.begin());
+            }
+            if ((rc = upload(ctx, &rm.d, tab.data(), sizeof(int) * tab.size()))) return rc;
+        }
+    }
 
     // activation canvases (ping-pong), zero-initialised
     ctx->act_bytes = static_cast<size_t>(cw) * ch * 64 * sizeof(__half);
@@ -457,6 +522,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         p.canvas_h = ch;
         p.n_strips = n_strips;
         p.total_rows = static_cast<int>(total);
+        p.n_rows = ch;
         p.colflag = ctx->d_colflag;
         p.rowflag = ctx->d_rowflag;
         p.weights = static_cast<const uint8_t*>(ctx->d_wblob[k + 1]) +

@@ -86,20 +86,43 @@ __device__ __forceinline__ void stream_range(const ConvParams& p, uint32_t rank,
     lo = wlo + (whi - wlo) * q / n_streams;
     hi = wlo + (whi - wlo) * (q + 1) / n_streams;
 }
-// steps of a stream: every segment (rows of one strip) costs its rows plus two halo rows
-__device__ __forceinline__ int stream_steps(long long lo, long long hi, int ch) {
-    if (hi <= lo) return 0;
-    const int n_seg = static_cast<int>((hi - 1) / ch - lo / ch) + 1;
-    return static_cast<int>(hi - lo) + 2 * n_seg;
+// Rows of a layer.  Upstream's tiles overlap by 10 px but the network's receptive field keeps shrinking towards
+// the output, so late layers need fewer and fewer rows of every padded tile (a row r pixels outside the kept
+// region matters only to layers at least r convolutions before the end).  A layer works on its list of needed
+// canvas rows (`rowmap`, ascending; null = every row): virtual row index v -> virtual row number, and the length
+// of the run of consecutive rows starting there.  In reverse mode the list is walked backwards and rows are
+// numbered from the bottom (y' = CH-1-y), as everywhere in this kernel.
+struct RowSpace {
+    const int* rowmap;
+    const int* run_fwd;
+    const int* run_bwd;
+    int nr, ch;
+    bool rev;
+    __device__ RowSpace(const ConvParams& p)
+        : rowmap(p.rowmap), run_fwd(p.run_fwd), run_bwd(p.run_bwd), nr(p.n_rows), ch(p.canvas_h), rev(p.reverse != 0) {}
+    __device__ int row(int v) const { return !rowmap ? v : (rev ? ch - 1 - rowmap[nr - 1 - v] : rowmap[v]); }
+    __device__ int run(int v) const { return !rowmap ? nr - v : (rev ? run_bwd[nr - 1 - v] : run_fwd[v]); }
+};
+
+// steps of a stream: every segment (a run of consecutive rows of one strip) costs its rows plus two halo rows
+__device__ __forceinline__ int stream_steps(const RowSpace& rs, long long lo, long long hi) {
+    int steps = 0;
+    while (lo < hi) {
+        const int v = static_cast<int>(lo % rs.nr);
+        const long long n = min(static_cast<long long>(rs.run(v)), hi - lo);
+        steps += static_cast<int>(n) + 2;
+        lo += n;
+    }
+    return steps;
 }
 
 // Walks the steps of a stream: (strip, virtual row y, interior?).  Past the end it yields padding steps
 // (row -1 = outside the canvas, never interior) so that the two CTAs of a pair stay in lock-step.
 struct Cursor {
+    RowSpace rs;
     long long pos, hi;
-    int ch;
     int strip = 0, ya = 0, yb = -2, y = 0;
-    __device__ Cursor(long long lo_, long long hi_, int ch_) : pos(lo_), hi(hi_), ch(ch_) {}
+    __device__ Cursor(const RowSpace& rs_, long long lo_, long long hi_) : rs(rs_), pos(lo_), hi(hi_) {}
     __device__ bool next(int& strip_o, int& y_o, bool& new_segment) {
         new_segment = false;
         if (y > yb + 1) {
@@ -108,9 +131,10 @@ struct Cursor {
                 y_o = -1;
                 return false;
             }
-            strip = static_cast<int>(pos / ch);
-            ya = static_cast<int>(pos % ch);
-            const long long n = min(static_cast<long long>(ch - ya), hi - pos);
+            strip = static_cast<int>(pos / rs.nr);
+            const int v = static_cast<int>(pos % rs.nr);
+            ya = rs.row(v);
+            const long long n = min(static_cast<long long>(rs.run(v)), hi - pos);
             yb = ya + static_cast<int>(n) - 1;
             pos += n;
             y = ya - 1;
@@ -228,15 +252,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     const bool rev = p.reverse != 0;
 
     // steps per stream; in a pair both CTAs run the larger count (the shorter stream pads)
+    const RowSpace rspace(p);
     int U[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         long long lo, hi;
         stream_range<PAIR>(p, rank, s, lo, hi);
-        U[s] = stream_steps(lo, hi, CH);
+        U[s] = stream_steps(rspace, lo, hi);
         if constexpr (PAIR) {
             stream_range<PAIR>(p, rank ^ 1u, s, lo, hi);
-            U[s] = max(U[s], stream_steps(lo, hi, CH));
+            U[s] = max(U[s], stream_steps(rspace, lo, hi));
         }
     }
 
@@ -271,7 +296,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
             long long lo0, hi0, lo1, hi1;
             stream_range<PAIR>(p, rank, 0, lo0, hi0);
             stream_range<PAIR>(p, rank, 1, lo1, hi1);
-            Cursor cur0(lo0, hi0, CH), cur1(lo1, hi1, CH);
+            Cursor cur0(rspace, lo0, hi0), cur1(rspace, lo1, hi1);
             Sequencer seq(U[0], U[1]);
             const uint32_t full_base = PAIR ? mapa_u32(base + kBarAFull, 0) : (base + kBarAFull);   // the even CTA's barriers
             uint32_t i = 0;
@@ -395,7 +420,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const uint32_t empty_base = PAIR ? mapa_u32(base + kBarAccEmpty + 8 * grp * 3, 0) : (base + kBarAccEmpty + 8 * grp * 3);
         long long lo, hi;
         stream_range<PAIR>(p, rank, grp, lo, hi);
-        Cursor cur(lo, hi, CH);
+        Cursor cur(rspace, lo, hi);
         const int n_events = U[grp];   // events 0 .. U-1 (event e is completed by step e+1)
         // What an event needs besides its accumulator: the geometry of its canvas row and (tail) the residual
         // pixel it points to.  Body: one table byte, loaded before the accumulator wait (the group idles ~1000

@@ -19,7 +19,11 @@ constexpr int kConvThreads = 320;  // producer warp + MMA warp + 2 x 4 epilogue 
 struct ConvParams {
     int canvas_w, canvas_h;
     int n_strips;
-    int total_rows;             // n_strips * canvas_h  (strip-rows of work)
+    int total_rows;             // n_strips * n_rows  (strip-rows of work)
+    int n_rows;                 // canvas rows this layer computes (<= canvas_h)
+    const int* rowmap;          // [n_rows] those rows, ascending; null = all canvas_h rows
+    const int* run_fwd;         // [n_rows] length of the run of consecutive rows starting at entry i
+    const int* run_bwd;         // [n_rows] length of the run of consecutive rows ending at entry i
     const uint8_t* colflag;     // [canvas_w] 1 = pixel of a tile, 0 = gap column
     const uint8_t* rowflag;     // [canvas_h]
     const void* weights;        // pre-swizzled B operand blob of this layer (global memory)

@@ -40,7 +40,35 @@ def oracle_canvas(frame: np.ndarray, w: srvgg.Weights, tile: int, prepad: int, l
     return canvas
 
 
-def feature_report(dev: np.ndarray, ref: np.ndarray) -> dict:
+def needed_rows(h: int, scale: int, tile: int, prepad: int, layer: int) -> np.ndarray:
+    """Canvas rows the device computes after `layer` convolutions (bool [CH]).  Upstream keeps only the centre
+    of every padded tile, so a row r pixels outside the kept region only matters to layers with at least r
+    convolutions still to come (18 - layer); the device skips the others (reve_b200/csrc/api.cu:set_row_space)
+    and leaves stale values there."""
+    import reve_b200
+    _, ch, _, _, src_y, out_y = reve_b200.geometry(max(h, prepad + 1), h, scale, tile, prepad)
+    margin = 18 - layer
+    if margin >= prepad:
+        return np.ones(ch, bool)
+    need = np.zeros(ch, bool)
+    i = 0
+    while i < ch:
+        if src_y[i] < 0:
+            i += 1
+            continue
+        j = i
+        while j < ch and src_y[j] >= 0:
+            j += 1
+        kept = np.where(out_y[i:j] >= 0)[0] + i
+        need[max(i, kept[0] - margin):min(j, kept[-1] + 1 + margin)] = True
+        i = j
+    return need
+
+
+def feature_report(dev: np.ndarray, ref: np.ndarray, rows: np.ndarray | None = None) -> dict:
+    """`rows`: bool mask of the canvas rows to compare (see needed_rows)."""
+    if rows is not None:
+        dev, ref = dev[rows], ref[rows]
     err = np.abs(dev - ref)
     tol = 2e-2 + 2e-2 * np.abs(ref)
     bad = err > tol

@@ -11,7 +11,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from helpers import feature_report, oracle_canvas  # noqa: E402
+from helpers import feature_report, needed_rows, oracle_canvas  # noqa: E402
 from oracle import srvgg  # noqa: E402
 
 import reve_b200  # noqa: E402
@@ -31,7 +31,7 @@ def run_case(name, w_px, h_px, scale, tile, prepad, layers, env):
             t0 = time.time()
             dev = up.debug_features(frame, layer)
             ref = oracle_canvas(frame, wts, tile, prepad, layer)
-            rep = feature_report(dev, ref)
+            rep = feature_report(dev, ref, needed_rows(h_px, scale, tile, prepad, layer))
             good = rep["bad_frac"] == 0.0
             ok = ok and good
             print(f"  layer {layer:2d}: {'OK ' if good else 'BAD'} {json.dumps(rep)} ({time.time() - t0:.2f}s)", flush=True)
