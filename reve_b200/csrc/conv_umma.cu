@@ -98,6 +98,7 @@ struct RowSpace {
     const int* run_bwd;
     int nr, ch;
     bool rev;
+    __device__ RowSpace() {}
     __device__ RowSpace(const ConvParams& p)
         : rowmap(p.rowmap), run_fwd(p.run_fwd), run_bwd(p.run_bwd), nr(p.n_rows), ch(p.canvas_h), rev(p.reverse != 0) {}
     __device__ int row(int v) const { return !rowmap ? v : (rev ? ch - 1 - rowmap[nr - 1 - v] : rowmap[v]); }
@@ -105,7 +106,7 @@ struct RowSpace {
 };
 
 // steps of a stream: every segment (a run of consecutive rows of one strip) costs its rows plus two halo rows
-__device__ __forceinline__ int stream_steps(const RowSpace& rs, long long lo, long long hi) {
+__device__ __noinline__ int stream_steps(const RowSpace rs, long long lo, long long hi) {
     int steps = 0;
     while (lo < hi) {
         const int v = static_cast<int>(lo % rs.nr);
@@ -118,12 +119,27 @@ __device__ __forceinline__ int stream_steps(const RowSpace& rs, long long lo, lo
 
 // Walks the steps of a stream: (strip, virtual row y, interior?).  Past the end it yields padding steps
 // (row -1 = outside the canvas, never interior) so that the two CTAs of a pair stay in lock-step.
+// Start of the segment at virtual position pos: strip, first row and length, packed (20 | 20 | 24 bits) so the
+// result travels in registers.  Rare (a few times per launch) and deliberately out of line: the 64-bit divisions
+// would otherwise be inlined into the producer's and the epilogue's per-step loops, and the hot loops of the warps
+// that share a scheduler have to stay within its instruction cache (measured: +7 % cycles per strip row).
+__device__ __noinline__ unsigned long long locate_segment(const int* rowmap, const int* run_fwd, const int* run_bwd,
+                                                          int nr, int ch, int rev, long long pos, long long hi) {
+    RowSpace rs;
+    rs.rowmap = rowmap; rs.run_fwd = run_fwd; rs.run_bwd = run_bwd; rs.nr = nr; rs.ch = ch; rs.rev = rev != 0;
+    const unsigned long long strip = static_cast<unsigned long long>(pos / nr);
+    const int v = static_cast<int>(pos % nr);
+    const unsigned long long ya = static_cast<unsigned long long>(rs.row(v));
+    const unsigned long long n = static_cast<unsigned long long>(min(static_cast<long long>(rs.run(v)), hi - pos));
+    return ya | (strip << 20) | (n << 40);
+}
+
 struct Cursor {
     RowSpace rs;
     long long pos, hi;
     int strip = 0, ya = 0, yb = -2, y = 0;
     __device__ Cursor(const RowSpace& rs_, long long lo_, long long hi_) : rs(rs_), pos(lo_), hi(hi_) {}
-    __device__ bool next(int& strip_o, int& y_o, bool& new_segment) {
+    __device__ __forceinline__ bool next(int& strip_o, int& y_o, bool& new_segment) {
         new_segment = false;
         if (y > yb + 1) {
             if (pos >= hi) {
@@ -131,11 +147,11 @@ struct Cursor {
                 y_o = -1;
                 return false;
             }
-            strip = static_cast<int>(pos / rs.nr);
-            const int v = static_cast<int>(pos % rs.nr);
-            ya = rs.row(v);
-            const long long n = min(static_cast<long long>(rs.run(v)), hi - pos);
-            yb = ya + static_cast<int>(n) - 1;
+            const unsigned long long seg = locate_segment(rs.rowmap, rs.run_fwd, rs.run_bwd, rs.nr, rs.ch, rs.rev, pos, hi);
+            ya = static_cast<int>(seg & 0xFFFFFu);
+            strip = static_cast<int>((seg >> 20) & 0xFFFFFu);
+            const int n = static_cast<int>(seg >> 40);
+            yb = ya + n - 1;
             pos += n;
             y = ya - 1;
             new_segment = true;
