@@ -29,6 +29,8 @@
 //     shared memory), which halves the B-operand shared-memory reads per SM; the even CTA issues.
 //   * Alternate layers sweep in opposite directions (`reverse`): the rows a CTA wrote last in
 //     layer l are the rows it reads first in layer l+1, while they may still be in L2.
+//   * Late layers skip the canvas rows no kept pixel depends on (RowSpace below): upstream keeps only
+//     the centre of every padded tile, so the work of a layer is a list of needed rows, not the canvas.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warp-
 // uniform code, one elected lane issues), warps 2..5 / 6..9 = epilogue group of stream 0 / 1
 // (TMEM -> registers -> zero the slot -> bias/PReLU -> fp16 -> swizzled smem -> TMA store, or for
