@@ -334,3 +334,42 @@ def test_yuv_format_error_paths():
             up.set_output_format(reve_b200.FMT_RGB24)          # frames in flight
         assert e.value.status == -7
         assert up.wait() == 1
+
+
+def _random_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n):
+        scale = int(rng.choice([2, 3, 4]))
+        prepad = int(rng.choice([0, 1, 3, 10, 10]))
+        w = int(rng.integers(max(2, prepad + 1), 260))
+        h = int(rng.integers(max(2, prepad + 1), 200))
+        tile = int(rng.choice([0, 32, 50, 64, 100, 200]))
+        grid = rng.choice(["", "1", "2", "5", "37"])
+        pairs = bool(rng.integers(0, 2))
+        cases.append((w, h, scale, tile, prepad, str(grid), pairs, int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("w,h,scale,tile,prepad,grid,pairs,seed", _random_cases(28, 2026),
+                         ids=lambda v: str(v))
+def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, pairs, seed, monkeypatch):
+    """Ragged sizes x tile sizes x pre-pads x scales x grid sizes x CTA pairs: every combination changes the
+    stream / segment / needed-row structure the kernels walk (one row per stream, streams spanning strips,
+    pre-pads shorter than the receptive field, a single CTA doing everything)."""
+    if grid:
+        monkeypatch.setenv("REVE_DEBUG_GRID", grid)
+    if pairs:
+        monkeypatch.setenv("REVE_CTA_PAIRS", "1")
+    wts = srvgg.make_weights(scale, seed % 1000)
+    model = reve_b200.Model.random(scale, seed % 1000)
+    frames = [srvgg.synthetic_frame(w, h, seed + i, "random" if i % 2 else "edges") for i in range(3)]
+    with reve_b200.Upscaler(model, w, h, tile=tile, prepad=prepad, ring_depth=3) as up:
+        outs = [np.empty((h * scale, w * scale, 3), np.uint8) for _ in frames]
+        for i, (f, o) in enumerate(zip(frames, outs)):      # three frames in flight = one stacked batch
+            up.submit(f, o, i)
+        assert [up.wait() for _ in frames] == [0, 1, 2]
+        single = up.upscale(frames[1])                       # and a batch of one
+    assert np.array_equal(single, outs[1])
+    for f, o in zip(frames[:2], outs[:2]):
+        check(o, srvgg.upscale(f, wts, tile=tile, prepad=prepad))
