@@ -373,3 +373,36 @@ def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, p
     assert np.array_equal(single, outs[1])
     for f, o in zip(frames[:2], outs[:2]):
         check(o, srvgg.upscale(f, wts, tile=tile, prepad=prepad))
+
+
+def test_device_resident_path_rgb_and_yuv():
+    """reve_upscale_device (frames already in HBM, what bench.py's `value` times): same bytes as the staged
+    path, in both output formats, for a frame count that is not a multiple of the launch batch."""
+    import torch
+    from oracle import colour
+    w, h, s, n = 112, 72, 2, 6
+    model = reve_b200.Model.random(s, 4)
+    frames = np.stack([srvgg.synthetic_frame(w, h, 30 + i, "random" if i % 2 else "edges") for i in range(n)])
+    with reve_b200.Upscaler(model, w, h, tile=50, prepad=10, ring_depth=4) as up:
+        ref = [up.upscale(f) for f in frames]
+        d_in = torch.from_numpy(frames).cuda()
+        d_out = torch.zeros((n, h * s, w * s, 3), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        up.upscale_device(d_in.data_ptr(), d_out.data_ptr(), n)
+        up.sync()
+        got = d_out.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], ref[i]), i
+        up.set_output_format(reve_b200.FMT_YUV420P10LE_BT709)
+        stride, nbytes = up.output_layout()
+        d_yuv = torch.zeros((n, nbytes), dtype=torch.uint8, device="cuda")
+        up.upscale_device(d_in.data_ptr(), d_yuv.data_ptr(), n)
+        up.sync()
+        raw = d_yuv.cpu().numpy()
+        W, H = w * s, h * s
+        for i in range(n):
+            y, u, v = colour.rgb_to_yuv420p10(ref[i], 709)
+            planes = raw[i].view("<u2")
+            assert np.array_equal(planes[:W * H].reshape(H, W), y)
+            assert np.array_equal(planes[W * H:W * H * 5 // 4].reshape(H // 2, W // 2), u)
+            assert np.array_equal(planes[W * H * 5 // 4:].reshape(H // 2, W // 2), v)
