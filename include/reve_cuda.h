@@ -140,6 +140,7 @@ typedef struct reve_profile {
     uint64_t frames;                   /* frames enqueued since reset */
     uint64_t body_frames;              /* sum over body launches of the frames each one processed */
     uint64_t launches_yuv;             /* colour-conversion kernels (one per frame when the output is YUV) */
+    uint64_t body_layer_frames;        /* sum over body launches of layers x frames (a chained launch runs several layers) */
 } reve_profile;
 /* on != 0: bracket every kernel launch with CUDA events (slower; for roofline measurements). */
 int reve_ctx_set_profiling(reve_ctx* ctx, int on);

@@ -12,7 +12,8 @@ class reve_profile(C.Structure):
     _fields_ = [("launches_conv0", C.c_uint64), ("launches_body", C.c_uint64),
                 ("launches_tail", C.c_uint64), ("ms_conv0", C.c_double), ("ms_body", C.c_double),
                 ("ms_tail", C.c_double), ("timed_body", C.c_uint64), ("timed_frames", C.c_uint64),
-                ("frames", C.c_uint64), ("body_frames", C.c_uint64), ("launches_yuv", C.c_uint64)]
+                ("frames", C.c_uint64), ("body_frames", C.c_uint64), ("launches_yuv", C.c_uint64),
+                ("body_layer_frames", C.c_uint64)]
 
 
 # name -> (restype, argtypes); mirrors include/reve_cuda.h one to one

@@ -80,6 +80,15 @@ struct reve_ctx {
     uint8_t* rgb_scratch[kMaxBatch] = {};   // tail output when the frame leaves as yuv420p10le
     int grid = 0;
     bool pair = false;    // body layers run as CTA pairs (tcgen05 cta_group::2)
+    // chained body layers (ChainParams in kernels.h): chain_len layers per launch, 0 = one launch per layer
+    int chain_len = 0;
+    int chain_strips = 0;
+    int n_chains = 0;
+    __half* d_chain_scratch = nullptr;
+    unsigned int* d_chain_flags = nullptr;
+    size_t chain_flag_bytes = 0;
+    CUtensorMap map_chain_scratch, map_chain_out[2];
+    ChainParams chain[kNumBody / 2];
     DebugBlock* dbg_host = nullptr;
     DebugBlock* dbg_dev = nullptr;
     long long* d_trace = nullptr;  // REVE_DEBUG_TRACE: timeline of CTA 0 of body layer 5
@@ -118,7 +127,11 @@ std::string cuda_msg(reve_ctx* ctx, const char* what, cudaError_t e) {
 
 int encode_map(reve_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base, int cw, int ch, int box_px) {
     const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(cw), static_cast<cuuint64_t>(ch)};
-    const cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(cw) * 128};
+    cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(cw) * 128};
+    // REVE_DEBUG_FLAGS bit4 (timing experiment, results are garbage): canvas rows alias each other 16 pixels
+    // apart, so a whole layer's activations stay in L2 -- the upper bound of any L2-residency scheme
+    if (const char* fe = std::getenv("REVE_DEBUG_FLAGS"))
+        if (std::atoi(fe) & 16) gstride[1] = 16 * 128;
     const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_px), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box, estr,
@@ -187,7 +200,7 @@ void set_row_space(const reve_ctx* ctx, ConvParams& p, int margin, int n, int ch
 // Enqueue the 18 launches of one batch (n <= ctx->batch frames stacked on the canvas, separated by
 // gap rows) on the compute stream.
 int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in_stride, uint8_t* const* d_out,
-                  long long out_stride, int stop_after_layers = kNumConv) {
+                  long long out_stride, int stop_after_layers = kNumConv, int* last_buf = nullptr) {
     const int ch = n * (ctx->frame_ch + 1) - 1;   // active canvas rows (the trailing gap row is excluded)
     prof_mark(ctx, -1);
     Conv0Params c0 = ctx->c0;
@@ -200,15 +213,44 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
     }
     ctx->prof.launches_conv0++;
     prof_mark(ctx, 0);
-    for (int k = 0; k < kNumBody && k + 1 < stop_after_layers; ++k) {
+    int cur = 0;   // canvas that holds the input of the next layer (conv0 wrote act[0])
+    for (int k = 0; k < kNumBody && k + 1 < stop_after_layers;) {
+        const int L = ctx->chain_len;
+        if (L > 1 && k % L == 0 && k + L < stop_after_layers) {
+            // layers k .. k+L-1 in one launch: canvas `cur` -> scratch rings (L2) -> canvas `cur ^ 1`
+            ChainParams c = ctx->chain[k / L];
+            ConvParams rows{};
+            set_row_space(ctx, rows, kNumBody - (k + L - 1), n, ch);   // the chain's last layer decides the rows
+            c.canvas_h = ch;
+            c.n_rows = rows.n_rows;
+            c.rowmap = rows.rowmap;
+            c.run_fwd = rows.run_fwd;
+            c.run_bwd = rows.run_bwd;
+            c.total_rows = ctx->chain_strips * c.n_rows;
+            const int chains = c.total_rows < ctx->n_chains ? c.total_rows : ctx->n_chains;
+            CK(ctx, cudaMemsetAsync(ctx->d_chain_flags, 0, ctx->chain_flag_bytes, ctx->s_comp));
+            CK(ctx, launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, c));
+            ctx->prof.launches_body++;
+            ctx->prof.body_frames += n;
+            ctx->prof.body_layer_frames += static_cast<uint64_t>(n) * L;
+            prof_mark(ctx, 1);
+            cur ^= 1;
+            k += L;
+            continue;
+        }
         ConvParams b = ctx->body[k];
+        // the sweep direction is baked into the layer's weight blob; the canvases alternate with every launch
         set_row_space(ctx, b, kNumBody - k, n, ch);   // body layer k is followed by 16 - k convolutions
         const int grid = b.total_rows < ctx->grid ? b.total_rows : ctx->grid;
-        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->pair && grid >= 2, ctx->map_in[k & 1], ctx->map_out[(k + 1) & 1], b));
+        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->pair && grid >= 2, ctx->map_in[cur], ctx->map_out[cur ^ 1], b));
         ctx->prof.launches_body++;
         ctx->prof.body_frames += n;
+        ctx->prof.body_layer_frames += n;
         prof_mark(ctx, 1);
+        cur ^= 1;
+        ++k;
     }
+    if (last_buf) *last_buf = cur;
     if (stop_after_layers >= kNumConv) {
         ConvParams t = ctx->tail;
         set_row_space(ctx, t, 0, n, ch);
@@ -220,7 +262,7 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
         }
         t.src_stride = in_stride;
         t.dst_stride = out_stride;
-        CK(ctx, launch_conv_tail(ctx->s_comp, grid, ctx->scale, ctx->map_in[0], t));
+        CK(ctx, launch_conv_tail(ctx->s_comp, grid, ctx->scale, ctx->map_in[cur], t));
         ctx->prof.launches_tail++;
         prof_mark(ctx, 2);
         if (yuv) {   // d_out[f] receives the packed planar frame: Y, then U, then V
@@ -324,6 +366,8 @@ void destroy_ctx(reve_ctx* ctx) {
     for (void* p : ctx->d_wblob) cudaFree(p);
     cudaFree(ctx->d_w0);
     cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_chain_scratch);
+    cudaFree(ctx->d_chain_flags);
     for (uint8_t* p : ctx->rgb_scratch) cudaFree(p);
     if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -541,6 +585,59 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         }
         if (!L.slope.empty())
             for (int c = 0; c < 64; c += 2) p.slope2[c >> 1] = __floats2half2_rn(L.slope[c], L.slope[c + 1]);
+    }
+
+    // chained body layers: REVE_CHAIN = 0 (off), 2 or 4 layers per launch
+    ctx->chain_len = 0;
+    if (const char* ce = std::getenv("REVE_CHAIN")) {
+        const int L = std::atoi(ce);
+        if (L == 2 || L == 4) ctx->chain_len = L;
+    }
+    if (ctx->pair || ctx->grid < ctx->chain_len) ctx->chain_len = 0;
+    if (ctx->chain_len) {
+        const int L = ctx->chain_len;
+        const int P = kBoxPx - 2 * L;
+        ctx->chain_strips = (cw + P - 1) / P;
+        ctx->n_chains = ctx->grid / L;
+        const size_t rows = chain_scratch_rows(ctx->n_chains, L);
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_chain_scratch), rows * 128));
+        CK(ctx, cudaMemset(ctx->d_chain_scratch, 0, rows * 128));
+        ctx->chain_flag_bytes = chain_flag_words(ctx->n_chains, L) * sizeof(unsigned int);
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_chain_flags), ctx->chain_flag_bytes));
+        {
+            const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
+            const cuuint64_t gstride[1] = {128};
+            const cuuint32_t box[2] = {64, 128};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = enc(&ctx->map_chain_scratch, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ctx->d_chain_scratch, gdim,
+                                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return set_err(ctx, REVE_E_CUDA, "cuTensorMapEncodeTiled (chain scratch map) failed");
+        }
+        for (int i = 0; i < 2; ++i)
+            if ((rc = encode_map(ctx, enc, &ctx->map_chain_out[i], ctx->act[i], cw, ch, P))) return rc;
+        for (int c = 0; c < kNumBody / L; ++c) {
+            ChainParams& p = ctx->chain[c];
+            p = ChainParams{};
+            p.canvas_w = cw;
+            p.canvas_h = ch;
+            p.n_strips = ctx->chain_strips;
+            p.n_rows = ch;
+            p.total_rows = ctx->chain_strips * ch;
+            p.colflag = ctx->d_colflag;
+            p.rowflag = ctx->d_rowflag;
+            p.len = L;
+            p.reverse = (dflags & 1u) ? 0 : ((c & 1) == 0);   // conv0 writes top-down, chain 0 sweeps bottom-up, ...
+            p.flags = ctx->d_chain_flags;
+            p.dbg = ctx->dbg_dev;
+            for (int j = 0; j < L; ++j) {
+                const int k = c * L + j;   // body layer
+                const ConvLayer& Lr = m.conv[k + 1];
+                p.weights[j] = static_cast<const uint8_t*>(ctx->d_wblob[k + 1]) + (p.reverse ? conv_weight_blob_bytes(64) : 0);
+                for (int o = 0; o < 64; ++o) p.bias[j][o] = Lr.b[o];
+                for (int o = 0; o < 64; o += 2) p.slope2[j][o >> 1] = __floats2half2_rn(Lr.slope[o], Lr.slope[o + 1]);
+            }
+        }
     }
 
     if (std::getenv("REVE_DEBUG_TRACE")) {
@@ -881,10 +978,11 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
     CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, ctx->g.in_h, cudaMemcpyHostToDevice, ctx->s_comp));
     const uint8_t* ins[1] = {s.d_in};
     uint8_t* outs[1] = {s.d_out};
-    int rc = enqueue_batch(ctx, 1, ins, static_cast<long long>(in_row), outs, static_cast<long long>(in_row) * ctx->scale, layer);
+    int buf = 0;
+    int rc = enqueue_batch(ctx, 1, ins, static_cast<long long>(in_row), outs, static_cast<long long>(in_row) * ctx->scale, layer, &buf);
     if (rc != REVE_OK) return rc;
     std::vector<__half> h(n);
-    CK(ctx, cudaMemcpyAsync(h.data(), ctx->act[(layer - 1) & 1], n * sizeof(__half), cudaMemcpyDeviceToHost, ctx->s_comp));
+    CK(ctx, cudaMemcpyAsync(h.data(), ctx->act[buf], n * sizeof(__half), cudaMemcpyDeviceToHost, ctx->s_comp));
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     for (size_t i = 0; i < n; ++i) {
         uint16_t bits;

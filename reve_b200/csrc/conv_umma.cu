@@ -108,12 +108,13 @@ struct RowSpace {
 };
 
 // steps of a stream: every segment (a run of consecutive rows of one strip) costs its rows plus two halo rows
-__device__ __noinline__ int stream_steps(const RowSpace rs, long long lo, long long hi) {
+// (chained layers: plus `ext` extra rows either side, see conv3x3_chain_kernel)
+__device__ __noinline__ int stream_steps(const RowSpace rs, long long lo, long long hi, int ext = 0) {
     int steps = 0;
     while (lo < hi) {
         const int v = static_cast<int>(lo % rs.nr);
         const long long n = min(static_cast<long long>(rs.run(v)), hi - lo);
-        steps += static_cast<int>(n) + 2;
+        steps += static_cast<int>(n) + 2 + 2 * ext;
         lo += n;
     }
     return steps;
@@ -624,6 +625,385 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     }
 }
 
+
+// ====================================================================================================
+// Chained body layers (ChainParams in kernels.h): CTA b computes layer j = b % len of chain b / len.
+//
+// All layers of a chain walk the SAME segments (those of the chain's last layer) in the same order with the same
+// two-stream interleave; layer j computes ext = len-1-j extra rows either side of every segment, so that what it
+// produces is exactly what layer j+1 consumes, step for step: the rows layer j completes (its valid events) are the
+// steps of layer j+1, in order, per stream.  Horizontally every layer works in the coordinates of the chain's 128-pixel
+// input box: layer j's valid output pixels are box rows 1+j .. 126-j, the last layer stores 128 - 2*len columns.
+//
+// Hand-over of one row (16 KB, already in the swizzled layout the next layer's UMMA descriptors expect):
+//   sender epilogue group: staging buffer -> TMA store into slot (row mod kChainSlots) of the link's scratch ring ->
+//     (one event later, after cp.async.bulk.wait_group 0) st.release.gpu published = rows stored so far;
+//   receiver loader thread: ld.acquire.gpu published >= row -> TMA load of the slot into its A ring ->
+//     (two steps later, when the load has landed) st.release.gpu consumed = row; the sender polls `consumed` before it
+//     overwrites a slot.
+// The scratch rings (kChainSlots x 16 KB per link and stream) are rewritten continuously and stay in L2: of the
+// 2 x len canvas passes that len separate layers cost, only one read and one write reach HBM.
+// Everything that is out of the canvas, in a gap row/column or outside a layer's valid pixel range is handed on as
+// zeros, which is what the next layer's SAME padding expects.
+struct ChainCursor {
+    RowSpace rs;
+    long long pos, hi;
+    int ext;
+    int strip = 0, ya = 0, yb = -2, y = 0;
+    __device__ ChainCursor(const RowSpace& rs_, long long lo_, long long hi_, int ext_) : rs(rs_), pos(lo_), hi(hi_), ext(ext_) {}
+    // (strip, virtual row y, interior?): y may lie up to ext+1 rows outside the canvas
+    __device__ __forceinline__ bool next(int& strip_o, int& y_o, bool& new_segment) {
+        new_segment = false;
+        if (y > yb + 1) {
+            if (pos >= hi) {
+                strip_o = strip;
+                y_o = -1;
+                return false;
+            }
+            const unsigned long long seg = locate_segment(rs.rowmap, rs.run_fwd, rs.run_bwd, rs.nr, rs.ch, rs.rev, pos, hi);
+            const int a = static_cast<int>(seg & 0xFFFFFu);
+            strip = static_cast<int>((seg >> 20) & 0xFFFFFu);
+            const int n = static_cast<int>(seg >> 40);
+            ya = a - ext;
+            yb = a + n - 1 + ext;
+            pos += n;
+            y = ya - 1;
+            new_segment = true;
+        }
+        strip_o = strip;
+        y_o = y;
+        const bool interior = (y >= ya) && (y <= yb);
+        ++y;
+        return interior;
+    }
+};
+
+enum : uint32_t { TAG_CHAIN_PUB = 7, TAG_CHAIN_CONS = 8 };
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                     const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ ChainParams p) {
+    constexpr int NG = 64;
+    constexpr int kStages = ring_stages(NG, false, false);
+    constexpr int kRowsDx = rows_per_dx(NG, false);
+    constexpr int kWBytes = w_smem_bytes(NG, false);
+    constexpr int kBank = 3 * NG;
+    constexpr int kTmemCols = tmem_cols(NG);
+    constexpr int kOffW = kCtrlBytes;
+    constexpr int kOffRing = kOffW + kWBytes + kGuard;
+    constexpr int kOffStage = kOffRing + kStages * kRowBytes + kGuard;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* const base_ptr = smem_raw + (base - raw);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    DebugBlock* const dbg = p.dbg;
+    const int C = p.len;
+    const int j = static_cast<int>(blockIdx.x) % C;          // layer of the chain this CTA computes
+    const unsigned chain = blockIdx.x / C;
+    const unsigned n_chains = gridDim.x / C;
+    const bool first = (j == 0), last = (j == C - 1);
+    const int ext = C - 1 - j;
+    const int P = kBoxPx - 2 * C;                            // output pixels per strip of the chain
+    const int CH = p.canvas_h;
+    const bool rev = p.reverse != 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(base + kBarW, 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(base + kBarAFull + 8 * s, 1);
+            mbar_init(base + kBarAEmpty + 8 * s, 1);
+        }
+        for (int s = 0; s < 6; ++s) {
+            mbar_init(base + kBarAccFull + 8 * s, 1);
+            mbar_init(base + kBarAccEmpty + 8 * s, 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(base + kTmemPtr, kTmemCols);
+        tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        if (first) prefetch_tmap(&in_map);
+        if (last) prefetch_tmap(&out_map);
+        if (C > 1) prefetch_tmap(&scratch_map);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kTmemPtr);
+
+    // the chain's block of strip-rows, cut into the two streams
+    RowSpace rspace;
+    rspace.rowmap = p.rowmap; rspace.run_fwd = p.run_fwd; rspace.run_bwd = p.run_bwd;
+    rspace.nr = p.n_rows; rspace.ch = CH; rspace.rev = rev;
+    long long lo[2], hi[2];
+    {
+        const unsigned b = rev ? (n_chains - 1 - chain) : chain;
+        const long long wlo = static_cast<long long>(b) * p.total_rows / n_chains;
+        const long long whi = static_cast<long long>(b + 1) * p.total_rows / n_chains;
+        lo[0] = wlo;
+        hi[0] = lo[1] = wlo + (whi - wlo) / 2;
+        hi[1] = whi;
+    }
+    int U[2];
+    U[0] = stream_steps(rspace, lo[0], hi[0], ext);
+    U[1] = stream_steps(rspace, lo[1], hi[1], ext);
+
+    // links: in = (j-1 -> j), out = (j -> j+1); per link and stream: kChainSlots scratch slots and two counters
+    const unsigned link_in = (chain * (C - 1) + (j - 1)) * 2, link_out = (chain * (C - 1) + j) * 2;
+
+    if (warp >= 2) {
+        const int grp = (warp - 2) >> 2;
+        const uint32_t t = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + grp * kBank;
+#pragma unroll
+        for (int c = 0; c < kBank / 16; ++c) tmem_st16_fill(t + c * 16, 0u);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader
+        if (lane == 0) {
+            mbar_arrive_expect_tx(base + kBarW, kWBytes);
+            bulk_load_1d(base + kOffW, p.weights[j], kWBytes, base + kBarW);
+            ChainCursor cur0(rspace, lo[0], hi[0], ext), cur1(rspace, lo[1], hi[1], ext);
+            Sequencer seq(U[0], U[1]);
+            int pub0 = 0, pub1 = 0;                 // last value seen of the two `published` counters
+            int ps_a = 0, pk_a = 0, ps_b = 0, pk_b = 0;   // (stream, row) of the loads issued one and two steps ago
+            uint32_t i = 0;
+            while (seq.next()) {
+                const uint32_t stage = i % kStages, use = i / kStages;
+                if (first) {
+                    int strip, y;
+                    bool newseg;
+                    if (seq.s == 0) cur0.next(strip, y, newseg); else cur1.next(strip, y, newseg);
+                    const int x = (rev ? p.n_strips - 1 - strip : strip) * P - C;
+                    mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                    mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
+                    tma_load_3d_hint(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage, 0,
+                                     x, rev ? CH - 1 - y : y, kPolicyEvictFirst);
+                } else {
+                    if (i >= 2) {   // the load issued two steps ago has landed: its scratch slot may be overwritten
+                        const uint32_t o = i - 2;
+                        mbar_wait(base + kBarAFull + 8 * (o % kStages), (o / kStages) & 1, dbg, TAG_A_FULL, o);
+                        st_release_gpu(p.flags + ((link_in + ps_b) * 2 + 1) * kChainFlagStride, static_cast<unsigned>(pk_b));
+                    }
+                    const int s = seq.s, k = seq.k;
+                    if (s == 0) flag_wait_ge(p.flags + ((link_in + 0) * 2 + 0) * kChainFlagStride, k, pub0, dbg, TAG_CHAIN_PUB);
+                    else        flag_wait_ge(p.flags + ((link_in + 1) * 2 + 0) * kChainFlagStride, k, pub1, dbg, TAG_CHAIN_PUB);
+                    fence_proxy_async_global();
+                    mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                    mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
+                    tma_load_2d(base + kOffRing + stage * kRowBytes, &scratch_map, base + kBarAFull + 8 * stage, 0,
+                                static_cast<int>(((link_in + s) * kChainSlots + (k - 1) % kChainSlots) * kBoxPx));
+                    ps_b = ps_a; pk_b = pk_a;
+                    ps_a = s; pk_a = k;
+                }
+                ++i;
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (as in conv3x3_umma_kernel)
+        mbar_wait(base + kBarW, 0, dbg, TAG_W);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(128, 3 * NG);
+        const uint64_t proto = umma_desc_sw128(0, 0);
+        const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
+        const uint32_t lo_flags = static_cast<uint32_t>(proto);
+        const uint32_t w_lo = lo_flags | ((base + kOffW) >> 4);
+        const uint32_t ring_lo = lo_flags | ((base + kOffRing) >> 4);
+        constexpr uint32_t kDx = kRowsDx * 8;
+        constexpr uint32_t kRot = NG * 8;
+        struct Gate { uint32_t bar_f, par_f, bar_e, par_e; bool need_e; };
+        auto gate_of = [&](uint32_t i, int s, int k) {
+            Gate g;
+            g.bar_f = base + kBarAFull + 8 * (i % kStages);
+            g.par_f = (i / kStages) & 1;
+            g.need_e = k >= 2;
+            g.bar_e = base + kBarAccEmpty + 8 * (s * 3 + (k + 1) % 3);
+            g.par_e = ((k - 2) / 3) & 1;
+            return g;
+        };
+        Sequencer seq(U[0], U[1]);
+        uint32_t i = 0;
+        bool have = seq.next();
+        if (have) {
+            const Gate g = gate_of(0, seq.s, seq.k);
+            mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, 0);
+            tc_fence_after();
+        }
+        const bool elected = elect_one();
+        while (have) {
+            const int s = seq.s, k = seq.k;
+            const uint32_t stage = i % kStages;
+            const uint32_t a_lo = ring_lo + stage * (kRowBytes >> 4);
+            uint32_t w_row = w_lo + (2 - (k + 1) % 3) * kRot;
+            asm volatile("" : "+r"(w_row));
+            const uint32_t d = tmem_base + s * kBank;
+            if (elected) {
+#pragma unroll
+                for (int dxk = 0; dxk < 4; ++dxk)
+                    umma_f16(d, mk_desc(desc_hi, a_lo - 8 + dxk * 2), mk_desc(desc_hi, w_row + dxk * 2), idesc, 1u);
+            }
+            have = seq.next();
+            Gate g{};
+            bool ok = true;
+            if (have) {
+                g = gate_of(i + 1, seq.s, seq.k);
+                ok = mbar_test_wait(g.bar_f, g.par_f);
+                if (g.need_e) ok = mbar_test_wait(g.bar_e, g.par_e) && ok;
+            }
+            if (elected) {
+#pragma unroll
+                for (int dxk = 4; dxk < 12; ++dxk) {
+                    const int dx = dxk >> 2, kk = dxk & 3;
+                    umma_f16(d, mk_desc(desc_hi, a_lo + (dx - 1) * 8 + kk * 2), mk_desc(desc_hi, w_row + dx * kDx + kk * 2), idesc, 1u);
+                }
+                umma_commit(base + kBarAEmpty + 8 * stage);
+                umma_commit(base + kBarAccFull + 8 * (s * 3 + (k - 1) % 3));
+            }
+            if (!ok) {
+                mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, i + 1);
+                if (g.need_e) mbar_wait(g.bar_e, g.par_e, dbg, TAG_ACC_EMPTY, seq.k);
+            }
+            tc_fence_after();
+            ++i;
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue warps
+        const int grp = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;       // pixel of the chain's 128-pixel box
+        const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * kBank;
+        ChainCursor cur(rspace, lo[grp], hi[grp], ext);
+        const int n_events = U[grp];
+        const int mlo = 1 + j, mhi = kBoxPx - 2 - j;     // valid output pixels of this layer
+        const bool gleader = (q == 0 && lane == 0);
+        unsigned int* const pub_flag = p.flags + ((link_out + grp) * 2 + 0) * kChainFlagStride;
+        const unsigned int* const cons_flag = p.flags + ((link_out + grp) * 2 + 1) * kChainFlagStride;
+        const int slot_base = static_cast<int>((link_out + grp) * kChainSlots);
+        const float* const bias = p.bias[j];
+        const __half2* const slope2 = p.slope2[j];
+        int sent = 0, cons_seen = 0;
+        int seg_xb = 0;
+        bool seg_colok = false;
+        for (int e = 0; e < n_events; ++e) {
+            bool valid = false, keep = false;
+            int pr = 0;
+            if (e >= 1) {
+                int strip, y;
+                bool newseg;
+                valid = cur.next(strip, y, newseg);
+                if (newseg) {
+                    seg_xb = (rev ? p.n_strips - 1 - strip : strip) * P - C;
+                    const int cx = seg_xb + m;
+                    const bool inside = (m >= mlo) && (m <= mhi) && (cx >= 0) && (cx < p.canvas_w);
+                    seg_colok = inside && (p.colflag[cx] != 0);
+                }
+                pr = rev ? CH - 1 - y : y;
+                if (valid) keep = seg_colok && (pr >= 0) && (pr < CH) && (p.rowflag[pr] != 0);
+            }
+            const int slot = e % 3;
+            mbar_wait(base + kBarAccFull + 8 * (grp * 3 + slot), (e / 3) & 1, dbg, TAG_ACC_FULL, e);
+            tc_fence_after();
+            uint32_t acc[NG];
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < NG / 16; ++c) {
+                    uint32_t(&dst)[16] = *reinterpret_cast<uint32_t(*)[16]>(&acc[c * 16]);
+                    tmem_ld16(tmem_lane + slot * NG + c * 16, dst);
+                }
+                tmem_wait_ld();
+            }
+#pragma unroll
+            for (int c = 0; c < NG / 16; ++c) tmem_st16_fill(tmem_lane + slot * NG + c * 16, 0u);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(base + kBarAccEmpty + 8 * (grp * 3 + slot));
+            if (!valid) continue;
+
+            const uint32_t stg = base + kOffStage + grp * kRowBytes;
+            if (gleader) {
+                if (last) {
+                    bulk_wait_read<0>();          // the previous row has left the staging buffer
+                } else {
+                    bulk_wait<0>();               // the previous row is in the scratch ring: publish it
+                    if (sent > 0) {
+                        fence_proxy_async_global();
+                        st_release_gpu(pub_flag, static_cast<unsigned>(sent));
+                    }
+                }
+            }
+            named_bar_sync(1 + grp, 128);
+            // last layer: box rows mlo..mhi become staging rows 0..P-1 (the stored box); other layers hand on the
+            // whole 128-row tile in place (rows outside the valid range as zeros)
+            const bool writes = last ? (m >= mlo && m <= mhi) : true;
+            if (writes) {
+                const int row = last ? m - mlo : m;
+                const uint32_t rbase = stg + row * 128;
+                if (keep) {
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int ch = c8 * 8 + jj * 2;
+                            const __half2 v = __floats2half2_rn(__uint_as_float(acc[ch]) + bias[ch],
+                                                                __uint_as_float(acc[ch + 1]) + bias[ch + 1]);
+                            const __half2 z = __float2half2_rn(0.f);
+                            const __half2 r = __hfma2(slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                            pk[jj] = *reinterpret_cast<const uint32_t*>(&r);
+                        }
+                        st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + (c8 << 4), 0u, 0u, 0u, 0u);
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + grp, 128);
+            if (gleader) {
+                if (last) {
+                    tma_store_3d(&out_map, stg, 0, seg_xb + C, pr);
+                } else {
+                    // slot (sent mod kChainSlots) last held row sent + 1 - kChainSlots of this stream
+                    flag_wait_ge(cons_flag, sent + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS);
+                    fence_proxy_async_global();
+                    tma_store_2d(&scratch_map, stg, 0, (slot_base + sent % kChainSlots) * kBoxPx);
+                }
+                bulk_commit();
+            }
+            ++sent;
+        }
+        if (!last && gleader) {
+            bulk_wait<0>();
+            if (sent > 0) {
+                fence_proxy_async_global();
+                st_release_gpu(pub_flag, static_cast<unsigned>(sent));
+            }
+        }
+    }
+
+    if (last && warp >= 2 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 template <int NG, bool TAIL, bool PAIR>
 constexpr size_t smem_bytes_t() {
     return 1024 /*alignment slack*/ + kCtrlBytes + w_smem_bytes(NG, PAIR) + kGuard +
@@ -668,7 +1048,15 @@ cudaError_t conv_kernels_init() {
     if ((e = set_smem_attr<64, false, true>()) != cudaSuccess) return e;
     if ((e = set_smem_attr<16, true, false>()) != cudaSuccess) return e;
     if ((e = set_smem_attr<32, true, false>()) != cudaSuccess) return e;
-    return set_smem_attr<48, true, false>();
+    if ((e = set_smem_attr<48, true, false>()) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv3x3_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem_bytes_t<64, false, false>()));
+}
+
+cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
+                              const CUtensorMap& scratch_map, const ChainParams& p) {
+    conv3x3_chain_kernel<<<grid, kConvThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map, scratch_map, p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map,

@@ -47,6 +47,38 @@ struct ConvParams {
     __half2 slope2[32];         // body: PReLU slopes as packed fp16 pairs (epilogue half2 math)
 };
 
+// Chained body layers: `len` consecutive 64->64 layers in ONE launch.  CTA b belongs to chain b / len and computes
+// layer b % len of it; a layer hands every finished row to the next one through a small scratch ring in global
+// memory that never leaves L2 (TMA store -> flag -> TMA load), so only the first layer reads the canvas and only the
+// last one writes it.  The strips of a chain are 128 - 2*len output pixels wide (each layer loses one halo column per
+// side), the rows of layer j extend len-1-j rows beyond the last layer's segments.
+constexpr int kChainMax = 4;
+constexpr int kChainSlots = 8;     // scratch ring slots per (chain, link, stream)
+constexpr int kChainFlagStride = 32;   // uint32 words between two flag counters (one 128-byte line each)
+struct ChainParams {
+    int canvas_w, canvas_h;
+    int n_strips;               // strips of 128 - 2*len output pixels
+    int total_rows;             // n_strips * n_rows
+    int n_rows;                 // canvas rows the LAST layer computes
+    const int* rowmap;          // as in ConvParams, for the last layer
+    const int* run_fwd;
+    const int* run_bwd;
+    const uint8_t* colflag;
+    const uint8_t* rowflag;
+    int len;                    // layers per chain (2 or 4)
+    int reverse;
+    unsigned int* flags;        // [chain][link][stream][published, consumed], kChainFlagStride words apart; zero at launch
+    DebugBlock* dbg;
+    const void* weights[kChainMax];
+    float bias[kChainMax][64];
+    __half2 slope2[kChainMax][32];
+};
+inline size_t chain_flag_words(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 4 * kChainFlagStride; }
+inline size_t chain_scratch_rows(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 2 * kChainSlots * kBoxPx; }
+// grid = n_chains * len CTAs, all of which must be resident at the same time (one per SM)
+cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
+                              const CUtensorMap& scratch_map, const ChainParams& p);
+
 // First convolution (3 -> 64) + PReLU on tensor cores (K = 27 padded to 32), fused with the u8 -> fp16
 // unpack, the reflect-101 pre-pad gather and the canvas layout (conv0.cu).
 struct Conv0Params {

@@ -163,6 +163,29 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
         : "memory");
 }
 
+// generic <-> async proxy ordering for global memory (TMA stores/loads vs flag loads/stores)
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded wait for a monotonic counter in global memory to reach `want` (`cache` = last value seen).
+__device__ __forceinline__ void flag_wait_ge(const unsigned int* p, int want, int& cache, DebugBlock* dbg, uint32_t tag) {
+    if (cache >= want) return;
+    const long long t0 = clock64();
+    for (;;) {
+        cache = static_cast<int>(ld_acquire_gpu(p));
+        if (cache >= want) return;
+        if (clock64() - t0 > (1ll << 32)) watchdog_fail(dbg, tag, static_cast<uint32_t>(want), static_cast<uint32_t>(cache));
+    }
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),

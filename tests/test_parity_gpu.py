@@ -48,6 +48,12 @@ def test_golden_vectors(path):
 
 
 @pytest.mark.parametrize("w,h,scale,tile,grid,pairs", [
+    (100, 30, 2, 0, "4", "chain4"),   # chained body layers: one chain of 4 CTAs (layer j -> j+1 through the L2 scratch rings)
+    (300, 40, 2, 0, "8", "chain4"),   # two chains, streams spanning several strips of 120 columns
+    (300, 200, 2, 0, None, "chain4"), # 37 chains
+    (200, 150, 2, 64, None, "chain4"),# tiles: gap rows/columns inside the extended rows of the inner layers
+    (137, 91, 3, 50, None, "chain2"), # chains of two layers (strips of 124 columns), x3
+    (500, 300, 2, 200, "6", "chain2"),# 3 chains of 2, needed-row lists with several segments per stream
     (100, 30, 2, 0, "1", False),      # one CTA, two streams walking the whole strip: every bank rotation, many ring laps
     (300, 40, 2, 0, "2", False),      # streams spanning two strips (several segments per stream)
     (300, 200, 2, 0, None, False),    # 148 CTAs, 2-3 rows per stream
@@ -61,8 +67,9 @@ def test_golden_vectors(path):
 def test_per_layer_features_and_output(w, h, scale, tile, grid, pairs, monkeypatch):
     if grid:
         monkeypatch.setenv("REVE_DEBUG_GRID", grid)
-    if pairs:
+    if pairs is True:
         monkeypatch.setenv("REVE_CTA_PAIRS", "1")
+    monkeypatch.setenv("REVE_CHAIN", pairs[5:] if isinstance(pairs, str) else "0")
     wts = srvgg.make_weights(scale, 1234)
     frame = srvgg.synthetic_frame(w, h, 5, "random")
     model = reve_b200.Model.random(scale, 1234)
