@@ -629,6 +629,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             p.len = L;
             p.reverse = (dflags & 1u) ? 0 : ((c & 1) == 0);   // conv0 writes top-down, chain 0 sweeps bottom-up, ...
             p.flags = ctx->d_chain_flags;
+            p.dflags = (dflags >> 5) & 7u;   // REVE_DEBUG_FLAGS bits 5..7 (experiments, see conv3x3_chain_kernel)
             p.dbg = ctx->dbg_dev;
             for (int j = 0; j < L; ++j) {
                 const int k = c * L + j;   // body layer
@@ -641,9 +642,16 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     }
 
     if (std::getenv("REVE_DEBUG_TRACE")) {
-        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_trace), 2048 * sizeof(long long)));
-        CK(ctx, cudaMemset(ctx->d_trace, 0, 2048 * sizeof(long long)));
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_trace), 4096 * sizeof(long long)));
+        CK(ctx, cudaMemset(ctx->d_trace, 0, 4096 * sizeof(long long)));
         if (std::string(std::getenv("REVE_DEBUG_TRACE")) == "tail") ctx->tail.trace = ctx->d_trace;
+        else if (ctx->chain_len) {   // chain 0 of the second chained launch, or of launch n with REVE_DEBUG_TRACE=c<n>
+            const char* te = std::getenv("REVE_DEBUG_TRACE");
+            int idx = (te[0] == 'c') ? std::atoi(te + 1) : 1;
+            if (idx < 0 || idx >= kNumBody / ctx->chain_len) idx = 1;
+            ctx->chain[idx].trace = ctx->d_trace;
+            if (const char* tc = std::getenv("REVE_DEBUG_TRACE_CHAIN")) ctx->chain[idx].trace_chain = std::atoi(tc);
+        }
         else ctx->body[5].trace = ctx->d_trace;
     }
 
@@ -994,7 +1002,7 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
 
 int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n) {
     if (!ctx || !out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
-    if (!ctx->d_trace || n > 2048) return set_err(ctx, REVE_E_INVAL, "tracing is off (set REVE_DEBUG_TRACE=1) or n > 2048");
+    if (!ctx->d_trace || n > 4096) return set_err(ctx, REVE_E_INVAL, "tracing is off (set REVE_DEBUG_TRACE=1) or n > 4096");
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     CK(ctx, cudaMemcpy(out, ctx->d_trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
     return REVE_OK;

@@ -65,7 +65,10 @@ constexpr int kBarAFull = 16;
 constexpr int kBarAEmpty = kBarAFull + 8 * kMaxStages;
 constexpr int kBarAccFull = kBarAEmpty + 8 * kMaxStages;   // [stream][slot]
 constexpr int kBarAccEmpty = kBarAccFull + 8 * 6;           // [stream][slot]
+constexpr int kBarStgFull = kBarAccEmpty + 8 * 6;          // chain kernel: [group] staging buffer written
+constexpr int kBarStgFree = kBarStgFull + 8 * 2;           // chain kernel: [group] staging buffer read by the TMA store
 constexpr int kTmemPtr = 512;
+static_assert(kBarStgFree + 8 * 2 <= kTmemPtr, "control block overflow");
 constexpr int kOffBias = 1024;   // 64 floats
 constexpr int kOffSlope = 1280;  // 64 floats
 static_assert(kBarAccEmpty + 8 * 6 <= kTmemPtr, "control block overflow");
@@ -387,6 +390,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, 0);
                 tc_fence_after();
             }
+            if (p.trace && lane == 0) p.trace[2048 + blockIdx.x * 4 + 1] = static_cast<long long>(globaltimer_ns());
             const bool elected = elect_one();
             while (have) {
                 const int s = seq.s, k = seq.k;
@@ -427,6 +431,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 }
                 tc_fence_after();
                 ++i;
+            }
+            if (p.trace && lane == 0) {   // per-CTA wall clock (ns): first step, end of the last step, steps | smid << 32
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                p.trace[2048 + blockIdx.x * 4 + 2] = static_cast<long long>(globaltimer_ns());
+                p.trace[2048 + blockIdx.x * 4 + 3] = static_cast<long long>(i) | (static_cast<long long>(smid) << 32);
             }
             __syncwarp();
         }
@@ -562,7 +572,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         }
                     } else {   // gap pixel (between tiles / frames): must read as zero in the next layer
 #pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + (c8 << 4), 0u, 0u, 0u, 0u);
+                        for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), 0u, 0u, 0u, 0u);
                     }
                 }
                 fence_proxy_async_smem();
@@ -636,11 +646,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 // input box: layer j's valid output pixels are box rows 1+j .. 126-j, the last layer stores 128 - 2*len columns.
 //
 // Hand-over of one row (16 KB, already in the swizzled layout the next layer's UMMA descriptors expect):
-//   sender epilogue group: staging buffer -> TMA store into slot (row mod kChainSlots) of the link's scratch ring ->
-//     (one event later, after cp.async.bulk.wait_group 0) st.release.gpu published = rows stored so far;
+//   sender epilogue group: staging buffer -> mbarrier -> the group's courier warp: TMA store into slot
+//     (row mod kChainSlots) of the link's scratch ring -> cp.async.bulk.wait_group 0 -> st.release.gpu published = rows
+//     stored so far (the global-memory round trips stay off the epilogue warps);
 //   receiver loader thread: ld.acquire.gpu published >= row -> TMA load of the slot into its A ring ->
-//     (two steps later, when the load has landed) st.release.gpu consumed = row; the sender polls `consumed` before it
-//     overwrites a slot.
+//     (two steps later, when the load has landed) consumed = row; the courier polls `consumed` before it overwrites a
+//     slot.
 // The scratch rings (kChainSlots x 16 KB per link and stream) are rewritten continuously and stay in L2: of the
 // 2 x len canvas passes that len separate layers cost, only one read and one write reach HBM.
 // Everything that is out of the canvas, in a gap row/column or outside a layer's valid pixel range is handed on as
@@ -678,9 +689,10 @@ struct ChainCursor {
     }
 };
 
-enum : uint32_t { TAG_CHAIN_PUB = 7, TAG_CHAIN_CONS = 8 };
+enum : uint32_t { TAG_CHAIN_PUB = 7, TAG_CHAIN_CONS = 8, TAG_STG_FULL = 9, TAG_STG_FREE = 10 };
+constexpr int kChainThreads = kConvThreads + 64;   // + one courier warp per epilogue group
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kChainThreads, 1)
 conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                      const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ ChainParams p) {
     constexpr int NG = 64;
@@ -721,6 +733,10 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             mbar_init(base + kBarAccFull + 8 * s, 1);
             mbar_init(base + kBarAccEmpty + 8 * s, 4);
         }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(base + kBarStgFull + 8 * s, 4);   // one arrive per warp of the group
+            mbar_init(base + kBarStgFree + 8 * s, 1);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -743,7 +759,8 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     rspace.nr = p.n_rows; rspace.ch = CH; rspace.rev = rev;
     long long lo[2], hi[2];
     {
-        const unsigned b = rev ? (n_chains - 1 - chain) : chain;
+        const unsigned cr = (p.dflags & 2u) ? (chain + 7) % n_chains : chain;   // experiment: which chain gets which block
+        const unsigned b = rev ? (n_chains - 1 - cr) : cr;
         const long long wlo = static_cast<long long>(b) * p.total_rows / n_chains;
         const long long whi = static_cast<long long>(b + 1) * p.total_rows / n_chains;
         lo[0] = wlo;
@@ -755,9 +772,10 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     U[1] = stream_steps(rspace, lo[1], hi[1], ext);
 
     // links: in = (j-1 -> j), out = (j -> j+1); per link and stream: kChainSlots scratch slots and two counters
-    const unsigned link_in = (chain * (C - 1) + (j - 1)) * 2, link_out = (chain * (C - 1) + j) * 2;
+    const unsigned chain_mem = (p.dflags & 1u) ? (chain + 5) % n_chains : chain;
+    const unsigned link_in = chain_mem * (C - 1) + (j - 1), link_out = chain_mem * (C - 1) + j;
 
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 10) {
         const int grp = (warp - 2) >> 2;
         const uint32_t t = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + grp * kBank;
 #pragma unroll
@@ -768,7 +786,51 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     __syncthreads();
     tc_fence_after();
 
-    if (warp == 0) {
+    if (warp >= 10) {
+        // ------------------------------------------------------------------ courier of epilogue group warp - 10
+        if (lane == 0 && !last) {
+            const int grp = warp - 10;
+            const int n_rows_out = stream_steps(rspace, lo[grp], hi[grp], ext - 1);   // = the next layer's steps
+            unsigned int* const pub_flag = p.flags + (link_out * 2 + 0) * kChainFlagStride + grp;
+            const unsigned int* const cons_flag = p.flags + (link_out * 2 + 1) * kChainFlagStride + grp;
+            const int slot_base = static_cast<int>((link_out * 2 + grp) * kChainSlots);
+            const uint32_t stg = base + kOffStage + grp * kRowBytes;
+            int cons_seen = 0;
+            long long* const tr = (p.trace && chain == static_cast<unsigned>(p.trace_chain) && grp == 0) ? p.trace + j * 512 + 500 : nullptr;
+            long long t_full = 0, t_store = 0, t_pub = 0;
+            for (int r = 0; r < n_rows_out; ++r) {
+                const long long c0 = tr ? clock64() : 0;
+                mbar_wait(base + kBarStgFull + 8 * grp, r & 1, dbg, TAG_STG_FULL, r);
+                const long long c1 = tr ? clock64() : 0;
+                // slot (r mod kChainSlots) last held row r - kChainSlots of this stream (rows are published 1-based)
+                if (flag_wait_ge(cons_flag, r + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS)) fence_proxy_async_global();
+                tma_store_2d(&scratch_map, stg, 0, (slot_base + r % kChainSlots) * kBoxPx);
+                bulk_commit();
+                bulk_wait_read<0>();
+                mbar_arrive(base + kBarStgFree + 8 * grp);
+                const long long c2 = tr ? clock64() : 0;
+                // publish the row before this one (its store has had a whole row period to complete): waiting for
+                // the store just issued would put its full latency into every iteration
+                // (a relaxed store: the rows it announces are complete, i.e. in L2, before it is issued; a gpu-scope
+                // release would wait for the store just issued as well -- measured 1450 cycles per row)
+                bulk_wait<1>();
+                if (r > 0) {
+                    fence_proxy_async_global();
+                    st_relaxed_gpu(pub_flag, static_cast<unsigned>(r));
+                }
+                if (tr) {
+                    const long long c3 = clock64();
+                    t_full += c1 - c0; t_store += c2 - c1; t_pub += c3 - c2;
+                }
+            }
+            bulk_wait<0>();
+            if (n_rows_out > 0) {
+                fence_proxy_async_global();
+                st_release_gpu(pub_flag, static_cast<unsigned>(n_rows_out));
+            }
+            if (tr) { tr[0] = t_full; tr[1] = t_store; tr[2] = t_pub; tr[3] = n_rows_out; }
+        }
+    } else if (warp == 0) {
         // ------------------------------------------------------------------ loader
         if (lane == 0) {
             mbar_arrive_expect_tx(base + kBarW, kWBytes);
@@ -777,14 +839,17 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             Sequencer seq(U[0], U[1]);
             int pub0 = 0, pub1 = 0;                 // last value seen of the two `published` counters
             int ps_a = 0, pk_a = 0, ps_b = 0, pk_b = 0;   // (stream, row) of the loads issued one and two steps ago
+            long long* const tr = (p.trace && chain == static_cast<unsigned>(p.trace_chain)) ? p.trace + j * 512 + 504 : nullptr;
+            long long t_poll = 0, t_empty = 0, t_retire = 0;
             uint32_t i = 0;
             while (seq.next()) {
                 const uint32_t stage = i % kStages, use = i / kStages;
+                const long long c0 = tr ? clock64() : 0;
                 if (first) {
                     int strip, y;
                     bool newseg;
                     if (seq.s == 0) cur0.next(strip, y, newseg); else cur1.next(strip, y, newseg);
-                    const int x = (rev ? p.n_strips - 1 - strip : strip) * P - C;
+                    int x = (rev ? p.n_strips - 1 - strip : strip) * P - C;
                     mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
                     mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
                     tma_load_3d_hint(base + kOffRing + stage * kRowBytes, &in_map, base + kBarAFull + 8 * stage, 0,
@@ -793,21 +858,35 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                     if (i >= 2) {   // the load issued two steps ago has landed: its scratch slot may be overwritten
                         const uint32_t o = i - 2;
                         mbar_wait(base + kBarAFull + 8 * (o % kStages), (o / kStages) & 1, dbg, TAG_A_FULL, o);
-                        st_release_gpu(p.flags + ((link_in + ps_b) * 2 + 1) * kChainFlagStride, static_cast<unsigned>(pk_b));
+                        // (ordered after the acquire on the mbarrier; no release needed: nothing of ours precedes it)
+                        st_relaxed_gpu(p.flags + (link_in * 2 + 1) * kChainFlagStride + ps_b, static_cast<unsigned>(pk_b));
                     }
+                    const long long c1 = tr ? clock64() : 0;
                     const int s = seq.s, k = seq.k;
-                    if (s == 0) flag_wait_ge(p.flags + ((link_in + 0) * 2 + 0) * kChainFlagStride, k, pub0, dbg, TAG_CHAIN_PUB);
-                    else        flag_wait_ge(p.flags + ((link_in + 1) * 2 + 0) * kChainFlagStride, k, pub1, dbg, TAG_CHAIN_PUB);
-                    fence_proxy_async_global();
+                    // one 64-bit load refreshes both streams' counters
+                    bool polled = false;
+                    if ((s == 0 ? pub0 : pub1) < k) {
+                        const unsigned int* const pf = p.flags + (link_in * 2 + 0) * kChainFlagStride;
+                        const long long t0 = clock64();
+                        do {
+                            ld_acquire_gpu_v2(pf, pub0, pub1);
+                            if (clock64() - t0 > (1ll << 32)) watchdog_fail(dbg, TAG_CHAIN_PUB, static_cast<uint32_t>(k), static_cast<uint32_t>(s == 0 ? pub0 : pub1));
+                        } while ((s == 0 ? pub0 : pub1) < k);
+                        polled = true;
+                    }
+                    if (polled) fence_proxy_async_global();
+                    const long long c2 = tr ? clock64() : 0;
                     mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                    if (tr) { const long long c3 = clock64(); t_retire += c1 - c0; t_poll += c2 - c1; t_empty += c3 - c2; }
                     mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, kRowBytes);
                     tma_load_2d(base + kOffRing + stage * kRowBytes, &scratch_map, base + kBarAFull + 8 * stage, 0,
-                                static_cast<int>(((link_in + s) * kChainSlots + (k - 1) % kChainSlots) * kBoxPx));
+                                static_cast<int>(((link_in * 2 + s) * kChainSlots + (k - 1) % kChainSlots) * kBoxPx));
                     ps_b = ps_a; pk_b = pk_a;
                     ps_a = s; pk_a = k;
                 }
                 ++i;
             }
+            if (tr) { tr[0] = t_retire; tr[1] = t_poll; tr[2] = t_empty; tr[3] = i; }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (as in conv3x3_umma_kernel)
@@ -833,12 +912,15 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         };
         Sequencer seq(U[0], U[1]);
         uint32_t i = 0;
+        long long* const cta_tr = (p.trace && lane == 0) ? p.trace + 2048 + blockIdx.x * 4 : nullptr;   // per-CTA: ns
+        if (cta_tr) cta_tr[0] = static_cast<long long>(globaltimer_ns());
         bool have = seq.next();
         if (have) {
             const Gate g = gate_of(0, seq.s, seq.k);
             mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, 0);
             tc_fence_after();
         }
+        if (cta_tr) cta_tr[1] = static_cast<long long>(globaltimer_ns());
         const bool elected = elect_one();
         while (have) {
             const int s = seq.s, k = seq.k;
@@ -847,6 +929,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             uint32_t w_row = w_lo + (2 - (k + 1) % 3) * kRot;
             asm volatile("" : "+r"(w_row));
             const uint32_t d = tmem_base + s * kBank;
+            if (p.trace && chain == static_cast<unsigned>(p.trace_chain) && i >= 200 && i < 700 && lane == 0) p.trace[j * 512 + i - 200] = clock64();
             if (elected) {
 #pragma unroll
                 for (int dxk = 0; dxk < 4; ++dxk)
@@ -876,6 +959,12 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             tc_fence_after();
             ++i;
         }
+        if (cta_tr) {
+            cta_tr[2] = static_cast<long long>(globaltimer_ns());
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            cta_tr[3] = static_cast<long long>(i) | (static_cast<long long>(smid) << 32);
+        }
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps
@@ -887,12 +976,9 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         const int n_events = U[grp];
         const int mlo = 1 + j, mhi = kBoxPx - 2 - j;     // valid output pixels of this layer
         const bool gleader = (q == 0 && lane == 0);
-        unsigned int* const pub_flag = p.flags + ((link_out + grp) * 2 + 0) * kChainFlagStride;
-        const unsigned int* const cons_flag = p.flags + ((link_out + grp) * 2 + 1) * kChainFlagStride;
-        const int slot_base = static_cast<int>((link_out + grp) * kChainSlots);
         const float* const bias = p.bias[j];
         const __half2* const slope2 = p.slope2[j];
-        int sent = 0, cons_seen = 0;
+        int sent = 0;
         int seg_xb = 0;
         bool seg_colok = false;
         for (int e = 0; e < n_events; ++e) {
@@ -932,18 +1018,12 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             if (!valid) continue;
 
             const uint32_t stg = base + kOffStage + grp * kRowBytes;
-            if (gleader) {
-                if (last) {
-                    bulk_wait_read<0>();          // the previous row has left the staging buffer
-                } else {
-                    bulk_wait<0>();               // the previous row is in the scratch ring: publish it
-                    if (sent > 0) {
-                        fence_proxy_async_global();
-                        st_release_gpu(pub_flag, static_cast<unsigned>(sent));
-                    }
-                }
+            if (last) {
+                if (gleader) bulk_wait_read<0>();          // the previous row has left the staging buffer
+                named_bar_sync(1 + grp, 128);
+            } else if (sent > 0) {
+                mbar_wait(base + kBarStgFree + 8 * grp, (sent - 1) & 1, dbg, TAG_STG_FREE, sent);   // courier has read row sent-1
             }
-            named_bar_sync(1 + grp, 128);
             // last layer: box rows mlo..mhi become staging rows 0..P-1 (the stored box); other layers hand on the
             // whole 128-row tile in place (rows outside the valid range as zeros)
             const bool writes = last ? (m >= mlo && m <= mhi) : true;
@@ -965,36 +1045,28 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                         }
                         st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                     }
-                } else {
+                } else {   // same chunk rotation as above: 8 consecutive rows hit 8 different bank groups (a plain
+                           // c8 << 4 is an 8-way bank conflict, measured +13 % per row in the right-edge strip)
 #pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + (c8 << 4), 0u, 0u, 0u, 0u);
+                    for (int c8 = 0; c8 < 8; ++c8) st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), 0u, 0u, 0u, 0u);
                 }
             }
             fence_proxy_async_smem();
-            named_bar_sync(1 + grp, 128);
-            if (gleader) {
-                if (last) {
+            if (last) {
+                named_bar_sync(1 + grp, 128);
+                if (gleader) {
                     tma_store_3d(&out_map, stg, 0, seg_xb + C, pr);
-                } else {
-                    // slot (sent mod kChainSlots) last held row sent + 1 - kChainSlots of this stream
-                    flag_wait_ge(cons_flag, sent + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS);
-                    fence_proxy_async_global();
-                    tma_store_2d(&scratch_map, stg, 0, (slot_base + sent % kChainSlots) * kBoxPx);
+                    bulk_commit();
                 }
-                bulk_commit();
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(base + kBarStgFull + 8 * grp);
             }
             ++sent;
         }
-        if (!last && gleader) {
-            bulk_wait<0>();
-            if (sent > 0) {
-                fence_proxy_async_global();
-                st_release_gpu(pub_flag, static_cast<unsigned>(sent));
-            }
-        }
     }
 
-    if (last && warp >= 2 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
+    if (last && warp >= 2 && warp < 10 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -1055,7 +1127,7 @@ cudaError_t conv_kernels_init() {
 
 cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
                               const CUtensorMap& scratch_map, const ChainParams& p) {
-    conv3x3_chain_kernel<<<grid, kConvThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map, scratch_map, p);
+    conv3x3_chain_kernel<<<grid, kChainThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map, scratch_map, p);
     return cudaGetLastError();
 }
 

@@ -67,13 +67,17 @@ struct ChainParams {
     const uint8_t* rowflag;
     int len;                    // layers per chain (2 or 4)
     int reverse;
-    unsigned int* flags;        // [chain][link][stream][published, consumed], kChainFlagStride words apart; zero at launch
+    unsigned int* flags;        // [chain][link][published | consumed][stream]: one 128-byte line per (link, kind), the two
+                                // streams' counters side by side (one 64-bit load reads both); zero at launch
     DebugBlock* dbg;
+    long long* trace;           // debug timeline of chain `trace_chain` (device memory, may be null)
+    int trace_chain;
+    unsigned int dflags;        // debug: bit0 = chain c uses the scratch rings / flags of chain (c + 5) mod n
     const void* weights[kChainMax];
     float bias[kChainMax][64];
     __half2 slope2[kChainMax][32];
 };
-inline size_t chain_flag_words(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 4 * kChainFlagStride; }
+inline size_t chain_flag_words(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 2 * kChainFlagStride; }
 inline size_t chain_scratch_rows(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 2 * kChainSlots * kBoxPx; }
 // grid = n_chains * len CTAs, all of which must be resident at the same time (one per SM)
 cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,

@@ -175,13 +175,25 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Bounded wait for a monotonic counter in global memory to reach `want` (`cache` = last value seen).
-__device__ __forceinline__ void flag_wait_ge(const unsigned int* p, int want, int& cache, DebugBlock* dbg, uint32_t tag) {
-    if (cache >= want) return;
+__device__ __forceinline__ void ld_acquire_gpu_v2(const unsigned int* p, int& a, int& b) {
+    asm volatile("ld.acquire.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded wait for a monotonic counter in global memory to reach `want` (`cache` = last value seen).  Returns
+// whether memory had to be read.
+__device__ __forceinline__ bool flag_wait_ge(const unsigned int* p, int want, int& cache, DebugBlock* dbg, uint32_t tag) {
+    if (cache >= want) return false;
     const long long t0 = clock64();
     for (;;) {
         cache = static_cast<int>(ld_acquire_gpu(p));
-        if (cache >= want) return;
+        if (cache >= want) return true;
         if (clock64() - t0 > (1ll << 32)) watchdog_fail(dbg, tag, static_cast<uint32_t>(want), static_cast<uint32_t>(cache));
     }
 }
