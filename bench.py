@@ -35,9 +35,9 @@ BODY_FLOP_PER_PX = 2 * 9 * 64 * 64                   # one 64->64 3x3 layer
 METRIC = "frames/s animevideov3 x2 1080p->4K"
 
 
-def measured_traffic():
+def measured_traffic(chained=False):
     """dram__bytes_read.sum + dram__bytes_write.sum of one body launch from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_body_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01_chain_traffic.json" if chained else "r01_body_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)
@@ -242,6 +242,7 @@ def run_ours(args):
     body_ms = pr["ms_body"] / max(1, pr["timed_body"])
     frames_timed = max(1, pr["frames"])
     frames_per_launch = pr["body_frames"] / max(1, pr["launches_body"])   # frames stacked per launch
+    layers_per_launch = pr["body_layer_frames"] / max(1, pr["body_frames"])  # chained launches run 2 or 4 layers
 
     # ---- end to end through reve_submit / reve_wait with pinned host buffers -------------------
     ring = up.ring_depth
@@ -286,7 +287,9 @@ def run_ours(args):
         fps = world * K * B / (ms / 1000.0)
         e2e_fps = world * K * B / e2e_s
         px = W_IN * H_IN
-        body_tflops = BODY_FLOP_PER_PX * px * frames_per_launch / (body_ms * 1e-3) / 1e12 if body_ms > 0 else 0.0
+        flop_per_launch = BODY_FLOP_PER_PX * px * frames_per_launch * layers_per_launch
+        body_tflops = flop_per_launch / (body_ms * 1e-3) / 1e12 if body_ms > 0 else 0.0
+        chained = layers_per_launch > 1.5
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         frame_tflops = fps / world * FLOP_PER_PX[SCALE] * px / 1e12
         line = {
@@ -307,19 +310,21 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * out_bytes, "api": "reve_submit/reve_wait, pinned host buffers",
                     "host_checksum": checksum},
             "gpu_launches": launches,
-            "roofline": {"kernel": "conv3x3_umma_kernel<64,false,false> (64->64 3x3 + PReLU, tcgen05, rotating TMEM banks)",
+            "roofline": {"kernel": (f"conv3x3_chain_kernel ({layers_per_launch:.0f} chained 64->64 3x3 + PReLU layers per launch, tcgen05, "
+                                    "rotating TMEM banks, layer-to-layer hand-over through L2 scratch rings)") if chained else
+                                   "conv3x3_umma_kernel<64,false,false> (64->64 3x3 + PReLU, tcgen05, rotating TMEM banks)",
                          "bound": "tensor", "achieved": body_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": body_tflops / peak,
-                         "traffic": (lambda t: None if not t else t["dram_bytes_per_launch"] * frames_per_launch / t["frames_per_launch"])(measured_traffic()),
-                         "traffic_unit": "bytes of DRAM read+write per launch (ncu capture profiles/r01_body_ncu_summary.txt); "
-                                         "algorithmic activation bytes per launch = 2 x 128 B x canvas pixels",
+                         "traffic": (lambda t: None if not t else t["dram_bytes_per_launch"] * frames_per_launch / t["frames_per_launch"])(measured_traffic(chained)),
+                         "traffic_unit": "bytes of DRAM read+write per launch (ncu capture under profiles/, see r01_body_traffic*.json); "
+                                         "algorithmic activation bytes per launch = 2 x 128 B x canvas pixels (one canvas read, one written)",
                          "peak_source": f"{psrc} bf16_tflops_sustained (kernel timed inside a long step)",
                          "avg_launch_ms": body_ms, "launches_timed": int(pr["timed_body"]),
                          "timed_in": "the timed region of `value` (every launch bracketed by CUDA events)" if prof_in_region
                                      else "a separate short pass (burst clocks)",
                          "kernel_ms_share_of_step": (pr["ms_conv0"] + pr["ms_body"] + pr["ms_tail"]) / ms if prof_in_region else None,
-                         "algorithmic_flop_per_launch": BODY_FLOP_PER_PX * px * frames_per_launch,
-                         "frames_per_launch": frames_per_launch,
+                         "algorithmic_flop_per_launch": flop_per_launch,
+                         "frames_per_launch": frames_per_launch, "layers_per_launch": layers_per_launch,
                          "ms_per_frame": {"conv0": pr["ms_conv0"] / frames_timed, "body_x16": pr["ms_body"] / frames_timed,
                                           "tail": pr["ms_tail"] / frames_timed}},
             "clocks": clocks,

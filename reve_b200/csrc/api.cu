@@ -82,6 +82,7 @@ struct reve_ctx {
     bool pair = false;    // body layers run as CTA pairs (tcgen05 cta_group::2)
     // chained body layers (ChainParams in kernels.h): chain_len layers per launch, 0 = one launch per layer
     int chain_len = 0;
+    bool chain_forced = false;   // REVE_CHAIN given: no small-batch fallback to single layers (tests)
     int chain_strips = 0;
     int n_chains = 0;
     __half* d_chain_scratch = nullptr;
@@ -216,7 +217,9 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
     int cur = 0;   // canvas that holds the input of the next layer (conv0 wrote act[0])
     for (int k = 0; k < kNumBody && k + 1 < stop_after_layers;) {
         const int L = ctx->chain_len;
-        if (L > 1 && k % L == 0 && k + L < stop_after_layers) {
+        // (a chain needs some rows per CTA to amortise its fill latency: tiny batches run layer by layer)
+        if (L > 1 && k % L == 0 && k + L < stop_after_layers &&
+            (ctx->chain_forced || static_cast<long long>(ctx->chain_strips) * ch >= 32ll * ctx->n_chains)) {
             // layers k .. k+L-1 in one launch: canvas `cur` -> scratch rings (L2) -> canvas `cur ^ 1`
             ChainParams c = ctx->chain[k / L];
             ConvParams rows{};
@@ -558,8 +561,11 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         p = ConvParams{};
-        // conv0 writes the canvas top-down, so body layer 0 sweeps bottom-up, layer 1 top-down, ...
-        p.reverse = (dflags & 1u) ? 0 : ((k & 1) == 0);
+        // Sweep direction per layer: it fixes the order in which the three vertical taps reach the fp32 accumulator,
+        // so it must not depend on the launch structure (single layers, chains of 2 or 4) or results would differ in
+        // the last bit between geometries.  Groups of four layers alternate: conv0 writes the canvas top-down, layers
+        // 0..3 sweep bottom-up, 4..7 top-down, ...; the tail (k = 16) sweeps bottom-up again.
+        p.reverse = (dflags & 1u) ? 0 : (((k >> 2) & 1) == 0);
         p.flags = (dflags & 4u) ? 1u : 0u;
         p.out = (k < kNumBody) ? ctx->act[(k + 1) & 1] : nullptr;
         p.canvas_w = cw;
@@ -587,11 +593,26 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             for (int c = 0; c < 64; c += 2) p.slope2[c >> 1] = __floats2half2_rn(L.slope[c], L.slope[c + 1]);
     }
 
-    // chained body layers: REVE_CHAIN = 0 (off), 2 or 4 layers per launch
-    ctx->chain_len = 0;
+    // Chained body layers (ChainParams in kernels.h): 4 or 2 layers per launch, whichever costs less.  A chain of L
+    // layers runs ~13 % (L = 4) / ~8 % (L = 2) faster per strip-row than L separate launches (measured at 1080p: the
+    // hand-over stays in L2 and the chip is power-bound), but its strips are 128 - 2L columns wide instead of 126, which
+    // can cost a whole extra strip.  REVE_CHAIN = 0 | 2 | 4 overrides the choice.
+    {
+        const double speed[3] = {1.0, 1.08, 1.13};
+        const int lens[3] = {0, 2, 4};
+        double best = 0;
+        for (int i = 0; i < 3; ++i) {
+            const int P = lens[i] ? kBoxPx - 2 * lens[i] : kStripPx;
+            const double cost = ((cw + P - 1) / P) / speed[i];
+            if (i == 0 || cost < best) { best = cost; ctx->chain_len = lens[i]; }
+        }
+    }
     if (const char* ce = std::getenv("REVE_CHAIN")) {
         const int L = std::atoi(ce);
-        if (L == 2 || L == 4) ctx->chain_len = L;
+        if (L == 0 || L == 2 || L == 4) {
+            ctx->chain_len = L;
+            ctx->chain_forced = true;
+        }
     }
     if (ctx->pair || ctx->grid < ctx->chain_len) ctx->chain_len = 0;
     if (ctx->chain_len) {
@@ -627,7 +648,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             p.colflag = ctx->d_colflag;
             p.rowflag = ctx->d_rowflag;
             p.len = L;
-            p.reverse = (dflags & 1u) ? 0 : ((c & 1) == 0);   // conv0 writes top-down, chain 0 sweeps bottom-up, ...
+            p.reverse = (dflags & 1u) ? 0 : ((((c * L) >> 2) & 1) == 0);   // the direction of its layers (see above)
             p.flags = ctx->d_chain_flags;
             p.dflags = (dflags >> 5) & 7u;   // REVE_DEBUG_FLAGS bits 5..7 (experiments, see conv3x3_chain_kernel)
             p.dbg = ctx->dbg_dev;

@@ -184,8 +184,10 @@ def test_device_resident_path_matches_submit_path():
         for i in range(n):
             assert np.array_equal(dev[i], up.upscale(frames[i]))
         prof = up.profile()
-        assert prof["frames"] == 2 * n and prof["body_frames"] == 16 * 2 * n
-        assert prof["launches_body"] == 16 * prof["launches_conv0"] == 16 * prof["launches_tail"]
+        # 16 body layers per frame whatever the launch structure (chained launches run 2 or 4 layers each)
+        assert prof["frames"] == 2 * n and prof["body_layer_frames"] == 16 * 2 * n
+        assert prof["launches_conv0"] == prof["launches_tail"]
+        assert prof["launches_body"] in (16 * prof["launches_conv0"], 8 * prof["launches_conv0"], 4 * prof["launches_conv0"])
 
 
 def test_results_are_deterministic_and_contexts_are_independent():
@@ -354,13 +356,14 @@ def _random_cases(n, seed):
         tile = int(rng.choice([0, 32, 50, 64, 100, 200]))
         grid = rng.choice(["", "1", "2", "5", "37"])
         pairs = bool(rng.integers(0, 2))
-        cases.append((w, h, scale, tile, prepad, str(grid), pairs, int(rng.integers(0, 1 << 30))))
+        chain = str(rng.choice(["0", "2", "4", "4"]))        # chained body layers (ignored with pairs / grids below 4)
+        cases.append((w, h, scale, tile, prepad, str(grid), pairs, chain, int(rng.integers(0, 1 << 30))))
     return cases
 
 
-@pytest.mark.parametrize("w,h,scale,tile,prepad,grid,pairs,seed", _random_cases(28, 2026),
+@pytest.mark.parametrize("w,h,scale,tile,prepad,grid,pairs,chain,seed", _random_cases(36, 2026),
                          ids=lambda v: str(v))
-def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, pairs, seed, monkeypatch):
+def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, pairs, chain, seed, monkeypatch):
     """Ragged sizes x tile sizes x pre-pads x scales x grid sizes x CTA pairs: every combination changes the
     stream / segment / needed-row structure the kernels walk (one row per stream, streams spanning strips,
     pre-pads shorter than the receptive field, a single CTA doing everything)."""
@@ -368,6 +371,7 @@ def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, p
         monkeypatch.setenv("REVE_DEBUG_GRID", grid)
     if pairs:
         monkeypatch.setenv("REVE_CTA_PAIRS", "1")
+    monkeypatch.setenv("REVE_CHAIN", chain)
     wts = srvgg.make_weights(scale, seed % 1000)
     model = reve_b200.Model.random(scale, seed % 1000)
     frames = [srvgg.synthetic_frame(w, h, seed + i, "random" if i % 2 else "edges") for i in range(3)]

@@ -45,8 +45,12 @@ def run(w, h, scale, tile, batch, frames=64):
 
 if __name__ == "__main__":
     cfgs = [(1280, 720, 4, 200), (960, 540, 3, 200), (640, 480, 2, 200), (1920, 1080, 2, 200), (1920, 1080, 2, 0)]
+    chains = sys.argv[1].split(",") if len(sys.argv) > 1 else [os.environ.get("REVE_CHAIN", "")]
     for (w, h, s, t) in cfgs:
+      for chain in chains:
+        if chain != "":
+            os.environ["REVE_CHAIN"] = chain
         for b in (1, 4):
-            fps, lat = run(w, h, s, t, b)
-            print(json.dumps({"frame": [w, h], "scale": s, "tile": t, "batch": b, "fps": round(fps, 1),
+            fps, lat = run(w, h, s, t, b, frames=256)
+            print(json.dumps({"frame": [w, h], "scale": s, "tile": t, "chain": chain, "batch": b, "fps": round(fps, 1),
                               "out_mpix_s": round(fps * w * h * s * s / 1e6, 1), "latency_ms_1frame": round(lat, 3)}), flush=True)
