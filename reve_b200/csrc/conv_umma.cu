@@ -795,7 +795,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             const unsigned int* const cons_flag = p.flags + (link_out * 2 + 1) * kChainFlagStride + grp;
             const int slot_base = static_cast<int>((link_out * 2 + grp) * kChainSlots);
             const uint32_t stg = base + kOffStage + grp * kRowBytes;
-            int cons_seen = 0;
+            int cons_seen = 0, published = 0;
             long long* const tr = (p.trace && chain == static_cast<unsigned>(p.trace_chain) && grp == 0) ? p.trace + j * 512 + 500 : nullptr;
             long long t_full = 0, t_store = 0, t_pub = 0;
             for (int r = 0; r < n_rows_out; ++r) {
@@ -809,14 +809,22 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                 bulk_wait_read<0>();
                 mbar_arrive(base + kBarStgFree + 8 * grp);
                 const long long c2 = tr ? clock64() : 0;
-                // publish the row before this one (its store has had a whole row period to complete): waiting for
-                // the store just issued would put its full latency into every iteration
-                // (a relaxed store: the rows it announces are complete, i.e. in L2, before it is issued; a gpu-scope
-                // release would wait for the store just issued as well -- measured 1450 cycles per row)
-                bulk_wait<1>();
-                if (r > 0) {
+                // Publish.  If the next row is already waiting, announce only the rows before this one (their stores have
+                // had a whole row period to complete) and move on; otherwise the courier would idle anyway, so it waits
+                // for this row's store as well and the next layer sees it one row period earlier.  The flag is a relaxed
+                // store: the rows it announces are complete, i.e. in L2, before it is issued (a gpu-scope release would
+                // also wait for the store just issued -- measured 1450 cycles per row).
+                int done = r;
+                if (r + 1 < n_rows_out && mbar_test_wait(base + kBarStgFull + 8 * grp, (r + 1) & 1)) {
+                    bulk_wait<1>();
+                } else {
+                    bulk_wait<0>();
+                    done = r + 1;
+                }
+                if (done > published) {
                     fence_proxy_async_global();
-                    st_relaxed_gpu(pub_flag, static_cast<unsigned>(r));
+                    st_relaxed_gpu(pub_flag, static_cast<unsigned>(done));
+                    published = done;
                 }
                 if (tr) {
                     const long long c3 = clock64();
@@ -824,7 +832,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                 }
             }
             bulk_wait<0>();
-            if (n_rows_out > 0) {
+            if (n_rows_out > published) {
                 fence_proxy_async_global();
                 st_release_gpu(pub_flag, static_cast<unsigned>(n_rows_out));
             }
