@@ -164,7 +164,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "CPU restatement of the reference path (oracle/srvgg.py); realesrgan-ncnn-vulkan itself is absent offline",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -334,12 +334,31 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
         elif world > 1:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     up.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_JSON_OUT = None
+
+
+def quiet_stdout():
+    """Libraries print to stdout (NCCL: 'NCCL version ...' when the first communicator is built); the contract is ONE
+    JSON line there.  File descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -357,9 +376,11 @@ def main():
                     help="time the kernels in a short separate pass instead of inside the timed region")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "ours" and args.gpus > 1 and world == 1):   # (the re-launching parent passes its children's stdout through)
+        quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
