@@ -7,10 +7,12 @@
 // no halo: the im2col row of a pixel already holds its 3x3x3 neighbourhood), N = 64.  Producer
 // warps build the im2col A tile straight from the u8 frame into shared memory (exact integers
 // 0..255 as fp16, canonical K-major no-swizzle core-matrix layout), one warp issues two K=16 MMAs
-// per tile into a ring of TMEM accumulators, and two epilogue groups apply (acc/255 + bias), PReLU,
+// per tile into a ring of TMEM accumulators, and three epilogue groups apply (acc/255 + bias), PReLU,
 // gap zeroing and write the row-major fp16 tile with one TMA store.
 // Warp roles (672 threads): warps 0-11 = three producer groups (tiles round-robin), warp 12 = TMEM
-// allocator + MMA issuer, warps 13-20 = two epilogue groups (alternate tiles).  The src_x / src_y
+// allocator + MMA issuer, warps 13-24 = three epilogue groups (tiles round-robin).  Measured: the kernel is bound
+// by warp-level throughput of producers AND epilogue together (3 + 3 groups: 0.121 ms per 1080p frame; 3 + 2: 0.131;
+// 4 + 2: 0.133; 2 + 4: 0.133), not by HBM (2.7 TB/s of writes).  The src_x / src_y
 // geometry tables are cached in shared memory so the gather needs one global round trip per tile.
 #include "kernels.h"
 
@@ -25,8 +27,9 @@ namespace {
 constexpr int kProducerGroups = 3;           // groups of 4 warps take tiles round-robin
 constexpr int kProducerWarps = 4 * kProducerGroups;
 constexpr int kMmaWarp = kProducerWarps;
-constexpr int kFirstEpiWarp = kMmaWarp + 1;  // 8 epilogue warps; TMEM lane quarter = warp % 4
-constexpr int kThreads = (kFirstEpiWarp + 8) * 32;
+constexpr int kFirstEpiWarp = kMmaWarp + 1;  // 4 * kEpiGroups epilogue warps; TMEM lane quarter = warp % 4
+constexpr int kEpiGroups = 3;                // epilogue groups of 4 warps, tiles round-robin
+constexpr int kThreads = (kFirstEpiWarp + 4 * kEpiGroups) * 32;
 constexpr int kMaxTableInts = 12288;         // src_x / src_y cached in shared memory when they fit (48 KB)
 constexpr int kStagesA = 6;             // multiple of kProducerGroups: a group always fills the same stages
 constexpr int kTileA = 128 * 64;       // 8 KB: 128 px x 32 k x fp16
@@ -45,7 +48,7 @@ constexpr int kCtrl = 1024;
 constexpr int kOffW = kCtrl;
 constexpr int kOffA = kOffW + kWBytes0;
 constexpr int kOffOut = kOffA + kStagesA * kTileA;
-constexpr int kOffTab = kOffOut + 2 * kStageOut;
+constexpr int kOffTab = kOffOut + kEpiGroups * kStageOut;
 constexpr int kSmem = 1024 + kOffTab + kMaxTableInts * 4;
 
 enum : uint32_t { TAG0_W = 11, TAG0_EMPTY = 12, TAG0_FULL = 13, TAG0_ACC_EMPTY = 14, TAG0_ACC_FULL = 15 };
@@ -66,14 +69,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// Two integers 0..255 as an fp16 pair without the quarter-rate I2F pipe: 0x6400 | v is the fp16 1024 + v
-// (ulp 1 in [1024, 2048)), and subtracting 1024 is exact.
-__device__ __forceinline__ uint32_t pack_u8x2(unsigned a, unsigned b) {
-    const uint32_t biased = 0x64006400u | a | (b << 16);
-    const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&biased), __float2half2_rn(1024.f));
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ Conv0Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -130,38 +125,60 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
             if ((j % kProducerGroups) != static_cast<uint32_t>(pg)) continue;
             const uint32_t stage = j % kStagesA, use = j / kStagesA;
             const unsigned px = static_cast<unsigned>(tile) * 128u + m;
-            uint32_t w[16];
+            // Every lane gathers its OWN canvas column for the three rows of the stencil (3 x 3 bytes); the left and
+            // right columns come from the neighbouring lanes by shuffle (consecutive lanes are consecutive canvas
+            // pixels), lanes 0 and 31 fetch the column beyond the warp themselves.  9 (+9 predicated) byte loads per
+            // pixel instead of 27: the kernel is instruction-issue-bound in exactly this code.
+            const bool in = px < npx;
+            const int cy = in ? static_cast<int>(px / static_cast<unsigned>(CW)) : 0;
+            const int cx = in ? static_cast<int>(px - static_cast<unsigned>(cy) * CW) : 0;
+            const int xe = (lane == 0) ? cx - 1 : cx + 1;                      // the extra column of lanes 0 / 31
+            const bool edge = (lane == 0) || (lane == 31);
+            const int sx = in ? tx[cx] : -1;
+            const int sxe = (edge && in && xe >= 0 && xe < CW) ? tx[xe] : -1;
+            const uint8_t* const fsrc = p.src[in ? max(tf[cy], 0) : 0];
+            uint32_t own[3], ext[3];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = 0u;
-            if (px < npx) {
-                const int cy = static_cast<int>(px / static_cast<unsigned>(CW)), cx = static_cast<int>(px - static_cast<unsigned>(cy) * CW);
-                if (tx[cx] >= 0 && ty[cy] >= 0) {
-                    unsigned v[28];
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int yy = cy + ky - 1;
-                        const int sy = (yy >= 0 && yy < CHh) ? ty[yy] : -1;   // -1 across a frame/tile gap
-                        const uint8_t* const fsrc = p.src[max(tf[cy], 0)];
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int xx = cx + kx - 1;
-                            const int sx = (xx >= 0 && xx < CW) ? tx[xx] : -1;
-                            const int t = (ky * 3 + kx) * 3;
-                            if (sy >= 0 && sx >= 0) {
-                                const uint8_t* s = fsrc + static_cast<long long>(sy) * p.src_stride + sx * 3;
-                                v[t] = s[0];
-                                v[t + 1] = s[1];
-                                v[t + 2] = s[2];
-                            } else {
-                                v[t] = v[t + 1] = v[t + 2] = 0u;
-                            }
-                        }
-                    }
-                    v[27] = 0u;
-#pragma unroll
-                    for (int i = 0; i < 14; ++i) w[i] = pack_u8x2(v[2 * i], v[2 * i + 1]);
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = cy + ky - 1;
+                const int sy = (in && yy >= 0 && yy < CHh) ? ty[yy] : -1;   // -1 across a frame/tile gap
+                const uint8_t* const row = fsrc + static_cast<long long>(max(sy, 0)) * p.src_stride;
+                own[ky] = 0u;
+                ext[ky] = 0u;
+                if (sy >= 0 && sx >= 0) {
+                    const uint8_t* s = row + sx * 3;
+                    own[ky] = s[0] | (static_cast<uint32_t>(s[1]) << 8) | (static_cast<uint32_t>(s[2]) << 16);
+                }
+                if (sy >= 0 && sxe >= 0) {
+                    const uint8_t* s = row + sxe * 3;
+                    ext[ky] = s[0] | (static_cast<uint32_t>(s[1]) << 8) | (static_cast<uint32_t>(s[2]) << 16);
                 }
             }
+            // a neighbouring lane is the neighbouring column only inside one canvas row
+            const bool has_l = cx > 0, has_r = cx < CW - 1;
+            uint32_t L[3], R[3];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, own[ky], 1);
+                const uint32_t dn = __shfl_down_sync(0xffffffffu, own[ky], 1);
+                L[ky] = (lane == 0) ? ext[ky] : (has_l ? up : 0u);
+                R[ky] = (lane == 31) ? ext[ky] : (has_r ? dn : 0u);
+            }
+            // the 27 bytes in im2col order k = (ky*3 + kx)*3 + c, packed four to a word, then two fp16 per word
+            const uint32_t q[7] = {L[0] | (own[0] << 24), (own[0] >> 8) | (R[0] << 16), (R[0] >> 16) | (L[1] << 8),
+                                   own[1] | (R[1] << 24), (R[1] >> 8) | (L[2] << 16), (L[2] >> 16) | (own[2] << 8), R[2]};
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                // bytes (b0, 0x64, b1, 0x64) = the fp16 pair (1024 + b0, 1024 + b1); subtracting 1024 is exact
+                const uint32_t lo = __byte_perm(q[i], 0x64646464u, 0x4140), hi = __byte_perm(q[i], 0x64646464u, 0x4342);
+                const __half2 k1024 = __float2half2_rn(1024.f);
+                const __half2 a = __hsub2(*reinterpret_cast<const __half2*>(&lo), k1024);
+                const __half2 b = __hsub2(*reinterpret_cast<const __half2*>(&hi), k1024);
+                w[2 * i] = *reinterpret_cast<const uint32_t*>(&a);
+                w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            w[14] = w[15] = 0u;
             mbar_wait(base + kBarEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG0_EMPTY, j);
             // element (row m, 16-byte k-chunk c) at (m/8)*512 + c*128 + (m%8)*16
             const uint32_t dst = base + kOffA + stage * kTileA + (m >> 3) * 512 + (m & 7) * 16;
@@ -206,11 +223,11 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const uint32_t stg = base + kOffOut + grp * kStageOut;
         const bool gleader = (q == 0 && lane == 0);
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-            if ((j & 1) != static_cast<uint32_t>(grp)) continue;
+            if ((j % kEpiGroups) != static_cast<uint32_t>(grp)) continue;
+            const uint32_t stg = base + kOffOut + grp * kStageOut;
             const uint32_t buf = j % kAccBufs, ubuf = j / kAccBufs;
             const unsigned px = static_cast<unsigned>(tile) * 128u + m;
             bool keep = false;
