@@ -9,7 +9,7 @@
 // 0..255 as fp16, canonical K-major no-swizzle core-matrix layout), one warp issues two K=16 MMAs
 // per tile into a ring of TMEM accumulators, and three epilogue groups apply (acc/255 + bias), PReLU,
 // gap zeroing and write the row-major fp16 tile with one TMA store.
-// Warp roles (672 threads): warps 0-11 = three producer groups (tiles round-robin), warp 12 = TMEM
+// Warp roles (800 threads): warps 0-11 = three producer groups (tiles round-robin), warp 12 = TMEM
 // allocator + MMA issuer, warps 13-24 = three epilogue groups (tiles round-robin).  Measured: the kernel is bound
 // by warp-level throughput of producers AND epilogue together (3 + 3 groups: 0.121 ms per 1080p frame; 3 + 2: 0.131;
 // 4 + 2: 0.133; 2 + 4: 0.133), not by HBM (2.7 TB/s of writes).  The src_x / src_y

@@ -11,7 +11,9 @@
 // (-g 0,1,..) the frames of the segment are dealt round-robin to one context per GPU (host thread
 // each; no collective).  The Rust crate of INTEGRATION.md does the same in-process.
 #include <dirent.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -21,6 +23,8 @@
 #include <map>
 #include <cstdio>
 #include <cstdlib>
+#include <cerrno>
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -135,6 +139,7 @@ void worker(const Options& o, const reve_model* model, int device, const std::ve
     }
     std::vector<size_t> mine;
     for (size_t idx = first; idx < names.size(); idx += step) mine.push_back(idx);
+    const auto t_ready = std::chrono::steady_clock::now();   // REVE_HOST_TIMING: the segment's frames/s without start-up
 
     // decode ahead of the GPU: results keyed by position in `mine`
     std::mutex dm;
@@ -206,22 +211,84 @@ void worker(const Options& o, const reve_model* model, int device, const std::ve
         // Pool destructors drain the remaining decode / encode tasks
     }
     reve_sync(ctx);
+    if (std::getenv("REVE_HOST_TIMING"))
+        std::fprintf(stderr, "[timing] gpu %d: %zu frames decoded, upscaled and encoded in %.1f ms after start-up\n", device, mine.size(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ready).count());
     for (int i = 0; i < depth; ++i) { reve_host_free(hin[i]); reve_host_free(hout[i]); }
     reve_ctx_destroy(ctx);
 }
 
-// Raw-frame staging: a stream of packed rgb24 frames in, upscaled rgb24
-// frames out, in order, with a ring of pinned buffers so the read of frame i+k, the kernels of frame i and the
-// write of frame i-k overlap.  This is what `ffmpeg -f rawvideo -pix_fmt rgb24 pipe:1` produces and what
-// `ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH -i pipe:0 -c:v libx265 ...` consumes (replacing the PNG export /
-// image2 input of reference reve-shared/src/lib.rs:93,100-119 and reve-cli/src/main.rs:297-300).
+// Blocking FIFO of ring-slot indices between the raw-mode threads (-1 = end of stream / failure).
+class SlotQueue {
+public:
+    void push(int v) {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(v); }
+        cv_.notify_one();
+    }
+    int pop() {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty(); });
+        const int v = q_.front();
+        q_.pop_front();
+        return v;
+    }
+    bool try_pop(int& v) {
+        std::lock_guard<std::mutex> l(m_);
+        if (q_.empty()) return false;
+        v = q_.front();
+        q_.pop_front();
+        return true;
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<int> q_;
+};
+
+bool read_full(int fd, uint8_t* p, size_t n, size_t& got) {
+    got = 0;
+    while (got < n) {
+        const ssize_t r = ::read(fd, p + got, n - got);
+        if (r == 0) return true;                 // end of stream
+        if (r < 0) { if (errno == EINTR) continue; return false; }
+        got += static_cast<size_t>(r);
+    }
+    return true;
+}
+bool write_full(int fd, const uint8_t* p, size_t n) {
+    while (n > 0) {
+        const ssize_t r = ::write(fd, p, n);
+        if (r < 0) { if (errno == EINTR) continue; return false; }
+        p += r;
+        n -= static_cast<size_t>(r);
+    }
+    return true;
+}
+
+// Raw streaming mode: rgb24 rawvideo frames in (what `ffmpeg -f rawvideo -pix_fmt rgb24 pipe:1`
+// emits), upscaled frames out (rgb24 or yuv420p10le, what `ffmpeg -f rawvideo ... -s WxH -i pipe:0 -c:v libx265 ...`
+// ingests) -- replacing the PNG export / image2 input of reference reve-shared/src/lib.rs:93,100-119 and
+// reve-cli/src/main.rs:297-300.  Three host
+// threads around one context: a reader fills pinned input buffers, this thread submits / waits (a reve_ctx is not
+// thread-safe), a writer drains pinned output buffers -- so the read of frame i+k, the kernels of frame i and the write
+// of frame i-k overlap, as decode and encode do in the reference's pipeline.
 int run_raw(const Options& o, const reve_model* model) {
-    FILE* fin = (o.in == "-") ? stdin : std::fopen(o.in.c_str(), "rb");
-    FILE* fout = (o.out == "-") ? stdout : std::fopen(o.out.c_str(), "wb");
-    if (!fin || !fout) { std::fprintf(stderr, "error: cannot open %s\n", !fin ? o.in.c_str() : o.out.c_str()); return 1; }
-    const int w = o.raw_w, h = o.raw_h, depth = 8;
+    const bool timing = std::getenv("REVE_HOST_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (timing) std::fprintf(stderr, "[timing] %s at %.1f ms\n", what,
+                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
+    const int fd_in = (o.in == "-") ? 0 : ::open(o.in.c_str(), O_RDONLY);
+    const int fd_out = (o.out == "-") ? 1 : ::open(o.out.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd_in < 0 || fd_out < 0) { std::fprintf(stderr, "error: cannot open %s\n", fd_in < 0 ? o.in.c_str() : o.out.c_str()); return 1; }
+#ifdef F_SETPIPE_SZ
+    ::fcntl(fd_in, F_SETPIPE_SZ, 1 << 20);    // no-ops (errors ignored) when the descriptor is not a pipe
+    ::fcntl(fd_out, F_SETPIPE_SZ, 1 << 20);
+#endif
+    const int w = o.raw_w, h = o.raw_h, ring = 8, depth = 12;   // 8 frames inside the library, 4 more being read / written
     reve_ctx* ctx = nullptr;
-    if (reve_ctx_create(o.gpus.empty() ? 0 : o.gpus[0], model, w, h, o.tile, o.prepad, depth, &ctx) != REVE_OK) {
+    if (reve_ctx_create(o.gpus.empty() ? 0 : o.gpus[0], model, w, h, o.tile, o.prepad, ring, &ctx) != REVE_OK) {
         std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr));
         return 1;
     }
@@ -242,37 +309,85 @@ int run_raw(const Options& o, const reve_model* model) {
             std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr));
             return 1;
         }
-    int rc = 0;
-    uint64_t submitted = 0, retired = 0;
-    auto retire = [&]() -> bool {
+    stamp("context and pinned buffers ready");
+    SlotQueue free_q, ready_q, done_q;
+    for (int i = 0; i < depth; ++i) free_q.push(i);
+    std::atomic<bool> failed{false};
+    std::vector<uint64_t> frame_no(depth, 0);
+
+    std::thread reader([&] {
+        for (uint64_t n = 0;; ++n) {
+            const int slot = free_q.pop();
+            if (slot < 0) break;                  // the other side failed
+            size_t got = 0;
+            if (!read_full(fd_in, hin[slot], in_bytes, got) || (got != 0 && got != in_bytes)) {
+                std::fprintf(stderr, "error: truncated frame %llu\n", (unsigned long long)n);
+                failed = true;
+                break;
+            }
+            if (got == 0) break;                  // end of stream
+            frame_no[slot] = n;
+            ready_q.push(slot);
+        }
+        ready_q.push(-1);
+    });
+    std::thread writer([&] {
+        for (;;) {
+            const int slot = done_q.pop();
+            if (slot < 0) break;
+            if (!failed && !write_full(fd_out, hout[slot], out_bytes)) {
+                std::fprintf(stderr, "error: short write\n");
+                failed = true;
+            }
+            if (o.verbose && !failed)
+                std::fprintf(stderr, "frame %llu -> frame %llu done\n", (unsigned long long)frame_no[slot], (unsigned long long)frame_no[slot]);
+            free_q.push(slot);
+        }
+    });
+
+    int inflight = 0;
+    bool eof = false;
+    while (!failed && (!eof || inflight > 0)) {
+        int slot = -2;
+        if (!eof && inflight < ring) {
+            if (inflight == 0) slot = ready_q.pop();            // nothing to wait for on the GPU: block on the reader
+            else if (!ready_q.try_pop(slot)) slot = -2;         // input not ready: retire a frame instead
+        }
+        if (slot == -1) { eof = true; continue; }
+        if (slot >= 0) {
+            if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], out_stride, static_cast<uint64_t>(slot)) != REVE_OK) {
+                std::fprintf(stderr, "error: %s\n", reve_last_error(ctx));
+                failed = true;
+                break;
+            }
+            ++inflight;
+            continue;
+        }
         uint64_t tag = 0;
-        if (reve_wait(ctx, &tag) != REVE_OK) { std::fprintf(stderr, "error: %s\n", reve_last_error(ctx)); return false; }
-        if (std::fwrite(hout[tag % depth], 1, out_bytes, fout) != out_bytes) { std::fprintf(stderr, "error: short write\n"); return false; }
-        if (o.verbose) std::fprintf(stderr, "frame %llu -> frame %llu done\n", (unsigned long long)tag, (unsigned long long)tag);
-        ++retired;
-        return true;
-    };
-    for (;;) {
-        if (submitted - retired == static_cast<uint64_t>(depth) && !retire()) { rc = 1; break; }
-        const int slot = static_cast<int>(submitted % depth);
-        const size_t got = std::fread(hin[slot], 1, in_bytes, fin);
-        if (got == 0) break;                       // end of stream
-        if (got != in_bytes) { std::fprintf(stderr, "error: truncated frame %llu\n", (unsigned long long)submitted); rc = 1; break; }
-        if (reve_submit(ctx, hin[slot], size_t(w) * 3, hout[slot], out_stride, submitted) != REVE_OK) {
+        if (reve_wait(ctx, &tag) != REVE_OK) {
             std::fprintf(stderr, "error: %s\n", reve_last_error(ctx));
-            rc = 1;
+            failed = true;
             break;
         }
-        ++submitted;
+        --inflight;
+        done_q.push(static_cast<int>(tag));
     }
-    while (rc == 0 && retired < submitted) if (!retire()) rc = 1;
-    std::fflush(fout);
     reve_sync(ctx);
+    stamp("last frame left the GPU");
+    done_q.push(-1);
+    writer.join();
+    stamp("last frame written");
+    if (failed) {
+        // the reader may sit in read() on a pipe whose other end stays open: do not wait for it
+        std::fflush(stderr);
+        std::_Exit(1);
+    }
+    reader.join();
     for (int i = 0; i < depth; ++i) { reve_host_free(hin[i]); reve_host_free(hout[i]); }
     reve_ctx_destroy(ctx);
-    if (fin != stdin) std::fclose(fin);
-    if (fout != stdout) std::fclose(fout);
-    return rc;
+    if (fd_in > 2) ::close(fd_in);
+    if (fd_out > 2) ::close(fd_out);
+    return 0;
 }
 
 }  // namespace
