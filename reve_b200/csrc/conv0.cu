@@ -12,7 +12,7 @@
 // Warp roles (800 threads): warps 0-11 = three producer groups (tiles round-robin), warp 12 = TMEM
 // allocator + MMA issuer, warps 13-24 = three epilogue groups (tiles round-robin).  Measured: the kernel is bound
 // by warp-level throughput of producers AND epilogue together (3 + 3 groups: 0.121 ms per 1080p frame; 3 + 2: 0.131;
-// 4 + 2: 0.133; 2 + 4: 0.133), not by HBM (2.7 TB/s of writes).  The src_x / src_y
+// 4 + 2: 0.133; 2 + 4: 0.133; 4 + 3: 0.125), not by HBM (2.7 TB/s of writes).  The src_x / src_y
 // geometry tables are cached in shared memory so the gather needs one global round trip per tile.
 #include "kernels.h"
 
@@ -24,14 +24,14 @@ namespace reve {
 
 namespace {
 
-constexpr int kProducerGroups = 4;           // groups of 4 warps take tiles round-robin
+constexpr int kProducerGroups = 3;           // groups of 4 warps take tiles round-robin
 constexpr int kProducerWarps = 4 * kProducerGroups;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kFirstEpiWarp = kMmaWarp + 1;  // 4 * kEpiGroups epilogue warps; TMEM lane quarter = warp % 4
 constexpr int kEpiGroups = 3;                // epilogue groups of 4 warps, tiles round-robin
 constexpr int kThreads = (kFirstEpiWarp + 4 * kEpiGroups) * 32;
 constexpr int kMaxTableInts = 12288;         // src_x / src_y cached in shared memory when they fit (48 KB)
-constexpr int kStagesA = 8;             // multiple of kProducerGroups: a group always fills the same stages
+constexpr int kStagesA = 6;             // multiple of kProducerGroups: a group always fills the same stages
 constexpr int kTileA = 128 * 64;       // 8 KB: 128 px x 32 k x fp16
 constexpr int kAccBufs = 4;            // TMEM accumulator ring: 4 x 64 columns
 constexpr int kWBytes0 = 64 * 64;      // 4 KB: 64 co x 32 k x fp16
