@@ -164,6 +164,15 @@ int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n);
 int reve_geometry(int in_w, int in_h, int scale, int tile, int prepad, int* canvas_w, int* canvas_h,
                   int* src_x, int* out_x, int* src_y, int* out_y, size_t cap);
 
+/* Launch structure the library chooses for a frame size (context-free, host only): the 16 body layers of
+ * SRVGGNetCompact run as chains of `layers_per_launch` (4, 2 or 1) layers per kernel launch whose activations are
+ * handed from SM to SM through L2-resident rings; a chain of L layers works on strips of 128 - 2L output columns
+ * (126 for single layers), so the choice depends on how many strips the canvas width needs.  launches_per_batch counts
+ * conv0 + body launches + tail.  The environment variable REVE_CHAIN = 0 | 2 | 4 overrides the choice when a context is
+ * created (0 = one launch per layer).  Any pointer may be NULL. */
+int reve_launch_plan(int in_w, int in_h, int scale, int tile, int prepad, int* layers_per_launch, int* strip_px,
+                     int* n_strips, int* launches_per_batch);
+
 #ifdef __cplusplus
 }
 #endif

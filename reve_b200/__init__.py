@@ -6,7 +6,7 @@ back to a CPU path: if the shared library or an sm_100 device is missing, it rai
 """
 from .segments import VideoState, last_segment_size, segment_table, shard_segments
 from .upscaler import (FMT_RGB24, FMT_YUV420P10LE_BT601, FMT_YUV420P10LE_BT709, Model, Upscaler, ReveError,
-                       load_library, library_path, geometry, upscale_segment)
+                       load_library, library_path, geometry, launch_plan, upscale_segment)
 
-__all__ = ["Model", "Upscaler", "ReveError", "load_library", "library_path", "geometry",
+__all__ = ["Model", "Upscaler", "ReveError", "load_library", "library_path", "geometry", "launch_plan",
            "upscale_segment", "FMT_RGB24", "FMT_YUV420P10LE_BT601", "FMT_YUV420P10LE_BT709", "segment_table", "last_segment_size", "shard_segments", "VideoState"]

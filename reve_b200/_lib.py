@@ -48,6 +48,7 @@ SIGNATURES = {
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "reve_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "reve_geometry": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 2 + [C.c_void_p] * 4 + [C.c_size_t]),
+    "reve_launch_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 4),
 }
 
 _lib = None

@@ -126,6 +126,26 @@ std::string cuda_msg(reve_ctx* ctx, const char* what, cudaError_t e) {
         if (e__ != cudaSuccess) return set_err(ctx, REVE_E_CUDA, cuda_msg(ctx, #call, e__)); \
     } while (0)
 
+// Chained body layers (ChainParams in kernels.h): 4 or 2 layers per launch, whichever costs less.  A chain of L
+// layers runs ~13 % (L = 4) / ~8 % (L = 2) faster per strip-row than L separate launches (measured at 1080p: the
+// hand-over stays in L2 and the chip is power-bound), but its strips are 128 - 2L columns wide instead of 126, which
+// can cost a whole extra strip.  REVE_CHAIN = 0 | 2 | 4 overrides the choice at context creation.
+int choose_chain_len(int canvas_w) {
+    const double speed[3] = {1.0, 1.08, 1.13};
+    const int lens[3] = {0, 2, 4};
+    double best = 0;
+    int len = 0;
+    for (int i = 0; i < 3; ++i) {
+        const int P = lens[i] ? kBoxPx - 2 * lens[i] : kStripPx;
+        const double cost = ((canvas_w + P - 1) / P) / speed[i];
+        if (i == 0 || cost < best) {
+            best = cost;
+            len = lens[i];
+        }
+    }
+    return len;
+}
+
 int encode_map(reve_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base, int cw, int ch, int box_px) {
     const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(cw), static_cast<cuuint64_t>(ch)};
     cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(cw) * 128};
@@ -593,20 +613,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             for (int c = 0; c < 64; c += 2) p.slope2[c >> 1] = __floats2half2_rn(L.slope[c], L.slope[c + 1]);
     }
 
-    // Chained body layers (ChainParams in kernels.h): 4 or 2 layers per launch, whichever costs less.  A chain of L
-    // layers runs ~13 % (L = 4) / ~8 % (L = 2) faster per strip-row than L separate launches (measured at 1080p: the
-    // hand-over stays in L2 and the chip is power-bound), but its strips are 128 - 2L columns wide instead of 126, which
-    // can cost a whole extra strip.  REVE_CHAIN = 0 | 2 | 4 overrides the choice.
-    {
-        const double speed[3] = {1.0, 1.08, 1.13};
-        const int lens[3] = {0, 2, 4};
-        double best = 0;
-        for (int i = 0; i < 3; ++i) {
-            const int P = lens[i] ? kBoxPx - 2 * lens[i] : kStripPx;
-            const double cost = ((cw + P - 1) / P) / speed[i];
-            if (i == 0 || cost < best) { best = cost; ctx->chain_len = lens[i]; }
-        }
-    }
+    ctx->chain_len = choose_chain_len(cw);
     if (const char* ce = std::getenv("REVE_CHAIN")) {
         const int L = std::atoi(ce);
         if (L == 0 || L == 2 || L == 4) {
@@ -1053,6 +1060,27 @@ int reve_geometry(int in_w, int in_h, int scale, int tile, int prepad, int* canv
         if (src_y) src_y[i] = g.y.src[i];
         if (out_y) out_y[i] = g.y.out[i];
     }
+    return REVE_OK;
+}
+
+int reve_launch_plan(int in_w, int in_h, int scale, int tile, int prepad, int* layers_per_launch, int* strip_px,
+                     int* n_strips, int* launches_per_batch) {
+    Geometry g;
+    std::string err;
+    int rc;
+    try {
+        rc = make_geometry(in_w, in_h, scale, tile, prepad, g, err);
+    } catch (const std::exception& e) {
+        rc = REVE_E_NOMEM;
+        err = e.what();
+    }
+    if (rc != REVE_OK) return set_err(nullptr, rc, err);
+    const int L = choose_chain_len(g.canvas_w());
+    const int P = L ? kBoxPx - 2 * L : kStripPx;
+    if (layers_per_launch) *layers_per_launch = L ? L : 1;
+    if (strip_px) *strip_px = P;
+    if (n_strips) *n_strips = (g.canvas_w() + P - 1) / P;
+    if (launches_per_batch) *launches_per_batch = 2 + kNumBody / (L ? L : 1);
     return REVE_OK;
 }
 

@@ -166,6 +166,15 @@ def geometry(in_w: int, in_h: int, scale: int, tile: int, prepad: int):
             arrs[2][:ch.value].copy(), arrs[3][:ch.value].copy())
 
 
+def launch_plan(in_w: int, in_h: int, scale: int, tile: int = 200, prepad: int = 10) -> dict:
+    """Launch structure chosen for a frame size (host only): body layers per launch, strip width, strips, launches."""
+    lib = _lib.load()
+    v = [C.c_int() for _ in range(4)]
+    _check(lib.reve_launch_plan(in_w, in_h, scale, tile, prepad, *[C.byref(x) for x in v]))
+    return {"layers_per_launch": v[0].value, "strip_px": v[1].value, "n_strips": v[2].value,
+            "launches_per_batch": v[3].value}
+
+
 class Upscaler:
     """One GPU context for a fixed input frame size.  tile=200, prepad=10 are the values the
     reference's spawned upscaler uses; tile=0 is the whole-frame variant."""

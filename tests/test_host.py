@@ -246,3 +246,22 @@ def test_pth_ingestion_rejects_foreign_checkpoints(lib):
     with pytest.raises(reve_b200.ReveError) as e:
         reve_b200.Model.from_state_dict(nan)
     assert e.value.status == -5
+
+
+def test_launch_plan_for_the_baseline_geometries():
+    """The body layers run as chains of 4, 2 or 1 layers per launch, chosen from the canvas width (include/reve_cuda.h,
+    reve_launch_plan): BASELINE.json's four frame sizes, tile 200 / pre-pad 10, and the whole-frame variant."""
+    plan = reve_b200.launch_plan
+    # 1080p: canvas 2129 columns -> 18 strips of 120 for chains of 4 (17 of 126 for single layers: the chain still wins)
+    assert plan(1920, 1080, 2) == {"layers_per_launch": 4, "strip_px": 120, "n_strips": 18, "launches_per_batch": 6}
+    assert plan(1280, 720, 4)["layers_per_launch"] == 4 and plan(1280, 720, 4)["n_strips"] == 12
+    assert plan(960, 540, 3) == {"layers_per_launch": 4, "strip_px": 120, "n_strips": 9, "launches_per_batch": 6}
+    # 480p: canvas 723 columns -> a chain of 4 would need 7 strips instead of 6: chains of 2 (strips of 124)
+    assert plan(640, 480, 2) == {"layers_per_launch": 2, "strip_px": 124, "n_strips": 6, "launches_per_batch": 10}
+    # whole-frame 1080p: canvas 1940 -> 16 strips of 124, 17 of 120
+    assert plan(1920, 1080, 2, tile=0)["layers_per_launch"] == 2
+    # a canvas narrower than one strip: nothing to lose, chains of 4
+    p1 = plan(40, 30, 2, tile=0)
+    assert p1["n_strips"] == 1 and p1["layers_per_launch"] == 4
+    with pytest.raises(reve_b200.ReveError):
+        plan(0, 10, 2)
