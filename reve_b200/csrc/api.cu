@@ -657,7 +657,6 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             p.len = L;
             p.reverse = (dflags & 1u) ? 0 : ((((c * L) >> 2) & 1) == 0);   // the direction of its layers (see above)
             p.flags = ctx->d_chain_flags;
-            p.dflags = (dflags >> 5) & 7u;   // REVE_DEBUG_FLAGS bits 5..7 (experiments, see conv3x3_chain_kernel)
             p.dbg = ctx->dbg_dev;
             for (int j = 0; j < L; ++j) {
                 const int k = c * L + j;   // body layer

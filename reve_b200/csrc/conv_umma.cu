@@ -777,8 +777,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     rspace.nr = p.n_rows; rspace.ch = CH; rspace.rev = rev;
     long long lo[2], hi[2];
     {
-        const unsigned cr = (p.dflags & 2u) ? (chain + 7) % n_chains : chain;   // experiment: which chain gets which block
-        const unsigned b = rev ? (n_chains - 1 - cr) : cr;
+        const unsigned b = rev ? (n_chains - 1 - chain) : chain;
         const long long wlo = static_cast<long long>(b) * p.total_rows / n_chains;
         const long long whi = static_cast<long long>(b + 1) * p.total_rows / n_chains;
         lo[0] = wlo;
@@ -790,8 +789,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     U[1] = stream_steps(rspace, lo[1], hi[1], ext);
 
     // links: in = (j-1 -> j), out = (j -> j+1); per link and stream: kChainSlots scratch slots and two counters
-    const unsigned chain_mem = (p.dflags & 1u) ? (chain + 5) % n_chains : chain;
-    const unsigned link_in = chain_mem * (C - 1) + (j - 1), link_out = chain_mem * (C - 1) + j;
+    const unsigned link_in = chain * (C - 1) + (j - 1), link_out = chain * (C - 1) + j;
 
     if (warp >= 2 && warp < 10) {
         const int grp = (warp - 2) >> 2;

@@ -72,7 +72,6 @@ struct ChainParams {
     DebugBlock* dbg;
     long long* trace;           // debug timeline of chain `trace_chain` (device memory, may be null)
     int trace_chain;
-    unsigned int dflags;        // debug: bit0 = chain c uses the scratch rings / flags of chain (c + 5) mod n
     const void* weights[kChainMax];
     float bias[kChainMax][64];
     __half2 slope2[kChainMax][32];
