@@ -707,6 +707,10 @@ struct ChainCursor {
     }
 };
 
+#ifndef REVE_PUBLISH_EVERY
+#define REVE_PUBLISH_EVERY 2
+#endif
+constexpr int kChainPublishEvery = REVE_PUBLISH_EVERY;   // rows per gpu-scope release (see the courier)
 enum : uint32_t { TAG_CHAIN_PUB = 7, TAG_CHAIN_CONS = 8, TAG_STG_FULL = 9, TAG_STG_FREE = 10 };
 constexpr int kChainThreads = kConvThreads + 64;   // + one courier warp per epilogue group
 
@@ -814,44 +818,44 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             int cons_seen = 0, published = 0;
             long long* const tr = (p.trace && chain == static_cast<unsigned>(p.trace_chain) && grp == 0) ? p.trace + j * 512 + 500 : nullptr;
             long long t_full = 0, t_store = 0, t_pub = 0;
+            // Announce rows 1..n of this stream to the next layer.  The rows were written by the async proxy (TMA);
+            // wait_group 0 makes them visible to this thread, the gpu-scope RELEASE store makes them visible to whoever
+            // acquires the counter.  (A relaxed store here loses the race about once in 1000 frames: the next layer then
+            // reads a partly stale ring slot -- tools/race_hunt.py.)  The release costs ~1300 cycles of this thread's
+            // time (a row period is ~2500, the store itself ~1000), so rows are announced kChainPublishEvery at a time,
+            // never while the next row is already waiting, and always before the courier blocks on `consumed`.
+            auto publish = [&](int n) {
+                if (n > published) {
+                    bulk_wait<0>();
+                    fence_proxy_async_global();
+                    st_release_gpu(pub_flag, static_cast<unsigned>(n));
+                    published = n;
+                }
+            };
             for (int r = 0; r < n_rows_out; ++r) {
                 const long long c0 = tr ? clock64() : 0;
                 mbar_wait(base + kBarStgFull + 8 * grp, r & 1, dbg, TAG_STG_FULL, r);
                 const long long c1 = tr ? clock64() : 0;
                 // slot (r mod kChainSlots) last held row r - kChainSlots of this stream (rows are published 1-based)
-                if (flag_wait_ge(cons_flag, r + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS)) fence_proxy_async_global();
+                if (cons_seen < r + 1 - kChainSlots) {
+                    publish(r);                                  // everything stored so far, before waiting for the consumer
+                    flag_wait_ge(cons_flag, r + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS);
+                    fence_proxy_async_global();
+                }
                 tma_store_2d(&scratch_map, stg, 0, (slot_base + r % kChainSlots) * kBoxPx);
                 bulk_commit();
                 bulk_wait_read<0>();
                 mbar_arrive(base + kBarStgFree + 8 * grp);
                 const long long c2 = tr ? clock64() : 0;
-                // Publish.  If the next row is already waiting, announce only the rows before this one (their stores have
-                // had a whole row period to complete) and move on; otherwise the courier would idle anyway, so it waits
-                // for this row's store as well and the next layer sees it one row period earlier.  The flag is a relaxed
-                // store: the rows it announces are complete, i.e. in L2, before it is issued (a gpu-scope release would
-                // also wait for the store just issued -- measured 1450 cycles per row).
-                int done = r;
-                if (r + 1 < n_rows_out && mbar_test_wait(base + kBarStgFull + 8 * grp, (r + 1) & 1)) {
-                    bulk_wait<1>();
-                } else {
-                    bulk_wait<0>();
-                    done = r + 1;
-                }
-                if (done > published) {
-                    fence_proxy_async_global();
-                    st_relaxed_gpu(pub_flag, static_cast<unsigned>(done));
-                    published = done;
-                }
+                if (r + 1 - published >= kChainPublishEvery &&
+                    !(r + 1 < n_rows_out && mbar_test_wait(base + kBarStgFull + 8 * grp, (r + 1) & 1)))
+                    publish(r + 1);
                 if (tr) {
                     const long long c3 = clock64();
                     t_full += c1 - c0; t_store += c2 - c1; t_pub += c3 - c2;
                 }
             }
-            bulk_wait<0>();
-            if (n_rows_out > published) {
-                fence_proxy_async_global();
-                st_release_gpu(pub_flag, static_cast<unsigned>(n_rows_out));
-            }
+            publish(n_rows_out);
             if (tr) { tr[0] = t_full; tr[1] = t_store; tr[2] = t_pub; tr[3] = n_rows_out; }
         }
     } else if (warp == 0) {
