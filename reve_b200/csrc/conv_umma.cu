@@ -707,9 +707,12 @@ struct ChainCursor {
     }
 };
 
+#ifndef REVE_PUBLISH_EVERY
+#define REVE_PUBLISH_EVERY 2
+#endif
+constexpr int kChainPublishEvery = REVE_PUBLISH_EVERY;   // rows per gpu-scope release (see the courier)
 enum : uint32_t { TAG_CHAIN_PUB = 7, TAG_CHAIN_CONS = 8, TAG_STG_FULL = 9, TAG_STG_FREE = 10 };
-constexpr int kChainThreads = kConvThreads + 64;   // + the courier warp and the publisher warp
-constexpr int kOffDone = 600;                       // control block: rows of each stream whose scratch store is complete
+constexpr int kChainThreads = kConvThreads + 64;   // + one courier warp per epilogue group
 
 __global__ void __launch_bounds__(kChainThreads, 1)
 conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
@@ -755,7 +758,6 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         for (int s = 0; s < 2; ++s) {
             mbar_init(base + kBarStgFull + 8 * s, 4);   // one arrive per warp of the group
             mbar_init(base + kBarStgFree + 8 * s, 1);
-            reinterpret_cast<volatile unsigned int*>(base_ptr + kOffDone)[s] = 0u;
         }
         fence_mbar_init();
     }
@@ -804,90 +806,57 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     __syncthreads();
     tc_fence_after();
 
-    if (warp == 11) {
-        // ------------------------------------------------------------------ publisher
-        // Announces rows to the next layer.  The rows were written by the async proxy (the courier's TMA stores); the
-        // courier's wait_group makes them visible to the courier, its shared-memory release store hands that knowledge
-        // to this thread, and the gpu-scope fence + flag store here make them visible to whoever acquires the counter
-        // (causality is cumulative).  Why a thread of its own: a relaxed announcement lost the race about once in 1000
-        // frames (the next layer read a partly stale ring slot: tools/race_hunt.py); the gpu-scope fence takes ~1300
-        // cycles, which a courier that also stores does not have every row (-7 %), and announcing every second row
-        // makes the hand-over bursty against an A ring of only four rows (-4.5 %).
+    if (warp >= 10) {
+        // ------------------------------------------------------------------ courier of epilogue group warp - 10
         if (lane == 0 && !last) {
-            int total[2], published[2] = {0, 0};
-            total[0] = stream_steps(rspace, lo[0], hi[0], ext - 1);   // = the next layer's steps
-            total[1] = stream_steps(rspace, lo[1], hi[1], ext - 1);
-            unsigned int* const pub = p.flags + (link_out * 2 + 0) * kChainFlagStride;
-            const long long t0 = clock64();
-            while (published[0] < total[0] || published[1] < total[1]) {
-                const int d0 = static_cast<int>(ld_acquire_cta_shared(base + kOffDone));
-                const int d1 = static_cast<int>(ld_acquire_cta_shared(base + kOffDone + 4));
-                if (d0 > published[0] || d1 > published[1]) {
+            const int grp = warp - 10;
+            const int n_rows_out = stream_steps(rspace, lo[grp], hi[grp], ext - 1);   // = the next layer's steps
+            unsigned int* const pub_flag = p.flags + (link_out * 2 + 0) * kChainFlagStride + grp;
+            const unsigned int* const cons_flag = p.flags + (link_out * 2 + 1) * kChainFlagStride + grp;
+            const int slot_base = static_cast<int>((link_out * 2 + grp) * kChainSlots);
+            const uint32_t stg = base + kOffStage + grp * kRowBytes;
+            int cons_seen = 0, published = 0;
+            long long* const tr = (p.trace && chain == static_cast<unsigned>(p.trace_chain) && grp == 0) ? p.trace + j * 512 + 500 : nullptr;
+            long long t_full = 0, t_store = 0, t_pub = 0;
+            // Announce rows 1..n of this stream to the next layer.  The rows were written by the async proxy (TMA);
+            // wait_group 0 makes them visible to this thread, the gpu-scope RELEASE store makes them visible to whoever
+            // acquires the counter.  (A relaxed store here loses the race about once in 1000 frames: the next layer then
+            // reads a partly stale ring slot -- tools/race_hunt.py.)  The release costs ~1300 cycles of this thread's
+            // time (a row period is ~2500, the store itself ~1000), so rows are announced kChainPublishEvery at a time,
+            // never while the next row is already waiting, and always before the courier blocks on `consumed`.
+            auto publish = [&](int n) {
+                if (n > published) {
+                    bulk_wait<0>();
                     fence_proxy_async_global();
-                    __threadfence();
-                    if (d0 > published[0]) st_relaxed_gpu(pub + 0, static_cast<unsigned>(d0));
-                    if (d1 > published[1]) st_relaxed_gpu(pub + 1, static_cast<unsigned>(d1));
-                    published[0] = d0;
-                    published[1] = d1;
-                } else {
-                    __nanosleep(32);
-                    if (clock64() - t0 > (1ll << 34)) watchdog_fail(dbg, TAG_CHAIN_PUB, static_cast<uint32_t>(published[0]), static_cast<uint32_t>(published[1]));
+                    st_release_gpu(pub_flag, static_cast<unsigned>(n));
+                    published = n;
                 }
-            }
-        }
-    } else if (warp == 10) {
-        // ------------------------------------------------------------------ courier (both epilogue groups)
-        // staging buffer -> scratch ring slot, in the order the rows become ready
-        if (lane == 0 && !last) {
-            int total[2], next[2] = {0, 0}, cons_seen[2] = {0, 0};
-            total[0] = stream_steps(rspace, lo[0], hi[0], ext - 1);
-            total[1] = stream_steps(rspace, lo[1], hi[1], ext - 1);
-            const unsigned int* const cons_flag = p.flags + (link_out * 2 + 1) * kChainFlagStride;
-            auto ready = [&](int g) { return next[g] < total[g] && mbar_test_wait(base + kBarStgFull + 8 * g, next[g] & 1); };
-            auto issue = [&](int g) {   // store row next[g] of group g
-                const int r = next[g];
-                // slot (r mod kChainSlots) last held row r - kChainSlots of this stream (rows are counted 1-based)
-                if (cons_seen[g] < r + 1 - kChainSlots) {
-                    flag_wait_ge(cons_flag + g, r + 1 - kChainSlots, cons_seen[g], dbg, TAG_CHAIN_CONS);
+            };
+            for (int r = 0; r < n_rows_out; ++r) {
+                const long long c0 = tr ? clock64() : 0;
+                mbar_wait(base + kBarStgFull + 8 * grp, r & 1, dbg, TAG_STG_FULL, r);
+                const long long c1 = tr ? clock64() : 0;
+                // slot (r mod kChainSlots) last held row r - kChainSlots of this stream (rows are published 1-based)
+                if (cons_seen < r + 1 - kChainSlots) {
+                    publish(r);                                  // everything stored so far, before waiting for the consumer
+                    flag_wait_ge(cons_flag, r + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS);
                     fence_proxy_async_global();
                 }
-                tma_store_2d(&scratch_map, base + kOffStage + g * kRowBytes, 0,
-                             static_cast<int>(((link_out * 2 + g) * kChainSlots + r % kChainSlots) * kBoxPx));
+                tma_store_2d(&scratch_map, stg, 0, (slot_base + r % kChainSlots) * kBoxPx);
                 bulk_commit();
-                ++next[g];
-            };
-            auto retire = [&](int g) {   // the store of group g's latest row has been read out of the staging buffer ...
-                mbar_arrive(base + kBarStgFree + 8 * g);
-            };
-            int g = 0;
-            const long long t0 = clock64();
-            while (next[0] < total[0] || next[1] < total[1]) {
-                if (!ready(g)) {
-                    g ^= 1;
-                    if (!ready(g)) {
-                        if (clock64() - t0 > (1ll << 34)) watchdog_fail(dbg, TAG_STG_FULL, static_cast<uint32_t>(next[0]), static_cast<uint32_t>(next[1]));
-                        continue;
-                    }
+                bulk_wait_read<0>();
+                mbar_arrive(base + kBarStgFree + 8 * grp);
+                const long long c2 = tr ? clock64() : 0;
+                if (r + 1 - published >= kChainPublishEvery &&
+                    !(r + 1 < n_rows_out && mbar_test_wait(base + kBarStgFull + 8 * grp, (r + 1) & 1)))
+                    publish(r + 1);
+                if (tr) {
+                    const long long c3 = clock64();
+                    t_full += c1 - c0; t_store += c2 - c1; t_pub += c3 - c2;
                 }
-                issue(g);
-                const int h = g ^ 1;
-                if (ready(h) && cons_seen[h] >= next[h] + 1 - kChainSlots) {   // the other group's row is waiting too: overlap the two
-                    issue(h);
-                    bulk_wait_read<1>();
-                    retire(g);
-                    bulk_wait_read<0>();
-                    retire(h);
-                } else {
-                    bulk_wait_read<0>();
-                    retire(g);
-                }
-                // ... and once it has arrived in the ring (shortly after) the publisher may announce it
-                bulk_wait<0>();
-                fence_proxy_async_global();
-                st_release_cta_shared(base + kOffDone, static_cast<unsigned>(next[0]));
-                st_release_cta_shared(base + kOffDone + 4, static_cast<unsigned>(next[1]));
-                g = h;
             }
+            publish(n_rows_out);
+            if (tr) { tr[0] = t_full; tr[1] = t_store; tr[2] = t_pub; tr[3] = n_rows_out; }
         }
     } else if (warp == 0) {
         // ------------------------------------------------------------------ loader

@@ -183,14 +183,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ unsigned int ld_acquire_cta_shared(uint32_t addr) {
-    unsigned int v;
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, unsigned int v) {
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
