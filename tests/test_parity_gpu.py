@@ -423,7 +423,9 @@ def test_chained_launches_are_race_free_under_load():
     """The chained body layers hand rows from SM to SM through global-memory rings guarded by flags (no cluster, no
     grid sync): a lost or early flag would show up as a frame that differs from the same frame computed a moment
     before.  400 full-size frames back to back (the GPU stays saturated, the power cap moves the clocks), every output
-    compared on the device with the first pass, which itself is checked against the oracle elsewhere."""
+    compared on the device with the first pass, which itself is checked against the oracle elsewhere.  (This test caught
+    a real one: rows announced with a relaxed store after cp.async.bulk.wait_group were read partly stale about once in
+    1000 frames; tools/race_hunt.py is the long-running version.)"""
     import torch
     w, h, s, n = 1920, 1080, 2, 8
     model = reve_b200.Model.random(s, 11)
