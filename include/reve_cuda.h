@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define REVE_VERSION 100 /* 0.1.0 */
+#define REVE_VERSION 200 /* 0.2.0 */
 
 typedef enum reve_status {
     REVE_OK = 0,
@@ -85,7 +85,56 @@ void reve_model_free(reve_model* m);
  * that may be in flight between reve_submit and reve_wait (1..16). */
 int reve_ctx_create(int device, const reve_model* m, int in_w, int in_h, int tile, int prepad,
                     int ring_depth, reve_ctx** out);
+
+/* Same with explicit options (everything the library decides by itself in reve_ctx_create can be pinned here; the
+ * library reads NO environment variables).  Zero-initialise, set struct_size = sizeof(reve_ctx_options), then the
+ * fields of interest.
+ *
+ * REVE_CTX_SHARED_DEVICE: other GPU work of this or another process may run on the device while this context is
+ * busy and the caller prefers kernels that never wait for one another: the 16 body layers then run as 16 separate
+ * launches.  Without the flag the body runs as chains of 4 (or 2) layers per launch whose CTAs hand rows to each other
+ * through L2 (about 10 % faster at 1080p).  That kernel is launched COOPERATIVELY, i.e. the driver starts it only once
+ * all of its CTAs can be resident together, so it is safe -- merely serialised -- next to a second context, the
+ * colour-conversion kernel or an MPS co-tenant; if the device cannot hold the grid at all (MIG slice, green context)
+ * the context silently uses the single-layer launches.  reve_ctx_launch_info reports which structure is in use. */
+#define REVE_CTX_SHARED_DEVICE 1u
+/* Test hooks (results stay correct unless stated): */
+#define REVE_DBG_NO_REVERSE 1u      /* every layer sweeps top-down (changes the last bit of some accumulations) */
+#define REVE_DBG_CTA_PAIRS 2u       /* body layers as CTA pairs driving tcgen05.mma.cta_group::2 (no chains) */
+#define REVE_DBG_SWAP_PAIR_B 4u     /* pairs load the wrong half of B: results are WRONG (negative test) */
+#define REVE_DBG_ALL_ROWS 8u        /* no needed-row lists: every layer computes every canvas row */
+#define REVE_DBG_ALIAS_ROWS 16u     /* canvas rows alias each other in L2: timing experiment, results are WRONG */
+#define REVE_DBG_FAULT 32u          /* chained kernel waits for a row that never comes: exercises the watchdog path */
+typedef struct reve_ctx_options {
+    uint32_t struct_size;      /* sizeof(reve_ctx_options) */
+    uint32_t flags;            /* REVE_CTX_* */
+    int layers_per_launch;     /* 0 = automatic (reve_launch_plan), 1 = one launch per layer, 2 / 4 = chains */
+    int max_batch;             /* 0 = automatic; frames stacked on the canvas per launch set (1..4) */
+    /* test hooks */
+    uint32_t debug_flags;      /* REVE_DBG_* */
+    int debug_grid;            /* 0 = one CTA per SM; n > 0 caps the persistent grids at n CTAs */
+    int trace;                 /* 0 = off; 1 = body layer 5 / the chained launch `trace_launch`; 2 = tail (reve_debug_trace) */
+    int trace_launch;          /* chained launch to trace (0 .. 16/L - 1) */
+    int trace_chain;           /* chain of that launch */
+} reve_ctx_options;
+int reve_ctx_create_ex(int device, const reve_model* m, int in_w, int in_h, int tile, int prepad,
+                       int ring_depth, const reve_ctx_options* opt, reve_ctx** out);
 void reve_ctx_destroy(reve_ctx* ctx);
+/* Launch structure in use: body layers per launch (1, 2 or 4), frames per launch set, CTAs of the body launch,
+ * whether the body launches are cooperative.  Any pointer may be NULL. */
+int reve_ctx_launch_info(const reve_ctx* ctx, int* layers_per_launch, int* batch, int* grid, int* cooperative);
+
+/* Failure semantics.  A kernel-side protocol fault (a wait that exceeds its watchdog, ~2^32 SM cycles) ends the launch
+ * with a trap after writing a diagnostic word to host-mapped memory; the call that notices it (reve_wait, reve_sync,
+ * reve_submit, ...) returns REVE_E_CUDA and reve_last_error(ctx) carries "kernel watchdog: wait tag T timed out in
+ * block B".  As after any asynchronous CUDA fault (Xid, ECC, illegal address) the error is STICKY: the CUDA primary
+ * context of that device is lost for the whole process, so every reve_ctx on the same device fails from then on
+ * (contexts on other devices are unaffected) and the frames in flight are lost.  Recovery without restarting the
+ * process: reve_ctx_destroy every context of that device (safe on a dead context), drop -- do not free -- the pinned
+ * buffers obtained from reve_host_alloc while that device was current, call reve_device_recover(device), then create
+ * contexts again and resubmit from the last frame whose reve_wait succeeded.  reve_model handles live in host memory
+ * and stay valid. */
+int reve_device_recover(int device);
 /* Geometry of the context: output frame size and scale. */
 int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale);
 
@@ -152,7 +201,7 @@ int reve_ctx_get_profile(reve_ctx* ctx, reve_profile* out, int reset);
  * (cap_floats = capacity).  canvas_w/h may be NULL.  Used by the per-layer parity tests. */
 int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, int layer,
                         float* out, size_t cap_floats, int* canvas_w, int* canvas_h);
-/* Test hook: with REVE_DEBUG_TRACE=1 in the environment at context creation, CTA 0 of body layer 5
+/* Test hook: with reve_ctx_options.trace = 1 at context creation, CTA 0 of body layer 5
  * records clock64() timestamps (MMA warp: out[i] at the start of step i, out[1000] = look-ahead misses;
  * epilogue group 0: out[1024 + 4*e + 0..3] = wait start / accumulator full / slot released / row stored of
  * event e); this copies the first n (<= 2048) words out.  See tools/gpu_trace.py. */
@@ -168,8 +217,8 @@ int reve_geometry(int in_w, int in_h, int scale, int tile, int prepad, int* canv
  * SRVGGNetCompact run as chains of `layers_per_launch` (4, 2 or 1) layers per kernel launch whose activations are
  * handed from SM to SM through L2-resident rings; a chain of L layers works on strips of 128 - 2L output columns
  * (126 for single layers), so the choice depends on how many strips the canvas width needs.  launches_per_batch counts
- * conv0 + body launches + tail.  The environment variable REVE_CHAIN = 0 | 2 | 4 overrides the choice when a context is
- * created (0 = one launch per layer).  Any pointer may be NULL. */
+ * conv0 + body launches + tail.  reve_ctx_options.layers_per_launch overrides the choice when a context is created.
+ * Any pointer may be NULL. */
 int reve_launch_plan(int in_w, int in_h, int scale, int tile, int prepad, int* layers_per_launch, int* strip_px,
                      int* n_strips, int* launches_per_batch);
 

@@ -16,6 +16,12 @@ class reve_profile(C.Structure):
                 ("body_layer_frames", C.c_uint64)]
 
 
+class reve_ctx_options(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("layers_per_launch", C.c_int),
+                ("max_batch", C.c_int), ("debug_flags", C.c_uint32), ("debug_grid", C.c_int), ("trace", C.c_int),
+                ("trace_launch", C.c_int), ("trace_chain", C.c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/reve_cuda.h one to one
 SIGNATURES = {
     "reve_version": (C.c_int, []),
@@ -31,7 +37,11 @@ SIGNATURES = {
     "reve_model_free": (None, [C.c_void_p]),
     "reve_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p)]),
+    "reve_ctx_create_ex": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(reve_ctx_options), C.POINTER(C.c_void_p)]),
     "reve_ctx_destroy": (None, [C.c_void_p]),
+    "reve_ctx_launch_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
+    "reve_device_recover": (C.c_int, [C.c_int]),
     "reve_ctx_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 5),
     "reve_ctx_set_output_format": (C.c_int, [C.c_void_p, C.c_int]),
     "reve_ctx_output_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

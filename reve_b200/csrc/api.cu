@@ -81,8 +81,10 @@ struct reve_ctx {
     int grid = 0;
     bool pair = false;    // body layers run as CTA pairs (tcgen05 cta_group::2)
     // chained body layers (ChainParams in kernels.h): chain_len layers per launch, 0 = one launch per layer
+    reve_ctx_options opt = {};   // as given to reve_ctx_create_ex (zero = automatic)
     int chain_len = 0;
-    bool chain_forced = false;   // REVE_CHAIN given: no small-batch fallback to single layers (tests)
+    bool chain_forced = false;   // layers_per_launch given: no small-batch fallback to single layers (tests)
+    bool chain_refused = false;  // a cooperative launch was refused at run time: single layers from then on
     int chain_strips = 0;
     int n_chains = 0;
     __half* d_chain_scratch = nullptr;
@@ -92,7 +94,7 @@ struct reve_ctx {
     ChainParams chain[kNumBody / 2];
     DebugBlock* dbg_host = nullptr;
     DebugBlock* dbg_dev = nullptr;
-    long long* d_trace = nullptr;  // REVE_DEBUG_TRACE: timeline of CTA 0 of body layer 5
+    long long* d_trace = nullptr;  // reve_ctx_options.trace: timeline of CTA 0 of body layer 5
     std::vector<Slot> ring;
     int head = 0, oldest = 0, inflight = 0;
     bool profiling = false;
@@ -129,7 +131,7 @@ std::string cuda_msg(reve_ctx* ctx, const char* what, cudaError_t e) {
 // Chained body layers (ChainParams in kernels.h): 4 or 2 layers per launch, whichever costs less.  A chain of L
 // layers runs ~13 % (L = 4) / ~8 % (L = 2) faster per strip-row than L separate launches (measured at 1080p: the
 // hand-over stays in L2 and the chip is power-bound), but its strips are 128 - 2L columns wide instead of 126, which
-// can cost a whole extra strip.  REVE_CHAIN = 0 | 2 | 4 overrides the choice at context creation.
+// can cost a whole extra strip.  reve_ctx_options.layers_per_launch overrides the choice at context creation.
 int choose_chain_len(int canvas_w) {
     const double speed[3] = {1.0, 1.08, 1.13};
     const int lens[3] = {0, 2, 4};
@@ -149,10 +151,9 @@ int choose_chain_len(int canvas_w) {
 int encode_map(reve_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base, int cw, int ch, int box_px) {
     const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(cw), static_cast<cuuint64_t>(ch)};
     cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(cw) * 128};
-    // REVE_DEBUG_FLAGS bit4 (timing experiment, results are garbage): canvas rows alias each other 16 pixels
+    // REVE_DBG_ALIAS_ROWS (timing experiment, results are garbage): canvas rows alias each other 16 pixels
     // apart, so a whole layer's activations stay in L2 -- the upper bound of any L2-residency scheme
-    if (const char* fe = std::getenv("REVE_DEBUG_FLAGS"))
-        if (std::atoi(fe) & 16) gstride[1] = 16 * 128;
+    if (ctx->opt.debug_flags & REVE_DBG_ALIAS_ROWS) gstride[1] = 16 * 128;
     const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_px), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box, estr,
@@ -238,7 +239,7 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
     for (int k = 0; k < kNumBody && k + 1 < stop_after_layers;) {
         const int L = ctx->chain_len;
         // (a chain needs some rows per CTA to amortise its fill latency: tiny batches run layer by layer)
-        if (L > 1 && k % L == 0 && k + L < stop_after_layers &&
+        if (L > 1 && !ctx->chain_refused && k % L == 0 && k + L < stop_after_layers &&
             (ctx->chain_forced || static_cast<long long>(ctx->chain_strips) * ch >= 32ll * ctx->n_chains)) {
             // layers k .. k+L-1 in one launch: canvas `cur` -> scratch rings (L2) -> canvas `cur ^ 1`
             ChainParams c = ctx->chain[k / L];
@@ -252,7 +253,17 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
             c.total_rows = ctx->chain_strips * c.n_rows;
             const int chains = c.total_rows < ctx->n_chains ? c.total_rows : ctx->n_chains;
             CK(ctx, cudaMemsetAsync(ctx->d_chain_flags, 0, ctx->chain_flag_bytes, ctx->s_comp));
-            CK(ctx, launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, c));
+            {
+                const cudaError_t le = launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, c);
+                if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+                    // the device (as partitioned right now) cannot hold the grid: nothing was launched; these layers
+                    // and every later batch run as single-layer launches, which never wait for another CTA
+                    (void)cudaGetLastError();
+                    ctx->chain_refused = true;
+                    continue;
+                }
+                CK(ctx, le);
+            }
             ctx->prof.launches_body++;
             ctx->prof.body_frames += n;
             ctx->prof.body_layer_frames += static_cast<uint64_t>(n) * L;
@@ -399,14 +410,22 @@ void destroy_ctx(reve_ctx* ctx) {
     delete ctx;
 }
 
-int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, int tile, int prepad, int ring_depth) {
+int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, int tile, int prepad, int ring_depth,
+               const reve_ctx_options& opt) {
+    ctx->opt = opt;
+    if (opt.layers_per_launch != 0 && opt.layers_per_launch != 1 && opt.layers_per_launch != 2 && opt.layers_per_launch != 4)
+        return set_err(ctx, REVE_E_INVAL, "layers_per_launch must be 0 (automatic), 1, 2 or 4");
+    if (opt.max_batch < 0 || opt.max_batch > kMaxBatch) return set_err(ctx, REVE_E_INVAL, "max_batch must be within 0..4");
+    if (opt.debug_grid < 0) return set_err(ctx, REVE_E_INVAL, "debug_grid must be >= 0");
     int ndev = 0;
     CK(ctx, cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return set_err(ctx, REVE_E_INVAL, "no such CUDA device");
     cudaDeviceProp prop;
     CK(ctx, cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return set_err(ctx, REVE_E_ARCH, std::string("device '") + prop.name + "' is not compute capability 10.x (sm_100); there is no fallback path");
+    // the library embeds sm_100a SASS only (arch-specific tcgen05 code does not run on 10.1 / 10.3 either)
+    if (prop.major != 10 || prop.minor != 0)
+        return set_err(ctx, REVE_E_ARCH, std::string("device '") + prop.name + "' is compute capability " + std::to_string(prop.major) + "." +
+                                             std::to_string(prop.minor) + ", not 10.0 (sm_100a); there is no fallback path");
     CK(ctx, cudaSetDevice(device));
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -432,10 +451,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     ctx->frame_ch = fch;
     ctx->batch = kMaxBatch < ring_depth ? kMaxBatch : ring_depth;
     while (ctx->batch > 1 && 2.0 * cw * (static_cast<double>(ctx->batch) * (fch + 1)) * 128.0 > 6e9) --ctx->batch;
-    if (const char* be = std::getenv("REVE_DEBUG_BATCH")) {
-        const int b = std::atoi(be);
-        if (b >= 1 && b < ctx->batch) ctx->batch = b;
-    }
+    if (opt.max_batch >= 1 && opt.max_batch < ctx->batch) ctx->batch = opt.max_batch;
     const int ch = ctx->batch * (fch + 1) - 1;   // canvas rows allocated
 
     // geometry tables (y tables repeated per stacked frame)
@@ -463,11 +479,9 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         rowpack[r] = (static_cast<uint32_t>(outy[r] + 1) << 17) | (static_cast<uint32_t>(srcy[r] + 1) << 2) |
                      static_cast<uint32_t>(rowframe[r] < 0 ? 0 : rowframe[r]);
     if ((rc = upload(ctx, &ctx->d_rowpack, rowpack.data(), sizeof(uint32_t) * ch))) return rc;
-    // needed-row lists (REVE_DEBUG_FLAGS bit3 disables them: every layer computes every row)
+    // needed-row lists (REVE_DBG_ALL_ROWS disables them: every layer computes every row)
     {
-        uint32_t df = 0;
-        if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) df = static_cast<uint32_t>(std::atoi(fe));
-        const int n_margins = (df & 8u) ? 0 : prepad;
+        const int n_margins = (opt.debug_flags & REVE_DBG_ALL_ROWS) ? 0 : prepad;
         ctx->rowmaps.resize(n_margins);
         for (int r = 0; r < n_margins; ++r) {
             std::vector<char> need(ch, 0);
@@ -550,8 +564,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     }
 
     // parameter blocks
-    uint32_t dflags = 0;
-    if (const char* fe = std::getenv("REVE_DEBUG_FLAGS")) dflags = static_cast<uint32_t>(std::atoi(fe));
+    const uint32_t dflags = opt.debug_flags;
     Conv0Params& c0 = ctx->c0;
     c0 = Conv0Params{};
     c0.canvas_w = cw;
@@ -570,14 +583,11 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     ctx->n_strips = n_strips;
     const long long total = static_cast<long long>(n_strips) * ch;
     ctx->grid = ctx->sm_count;   // persistent: one CTA per SM (clamped to the work of a batch at launch)
-    // Debug knob (tests only): cap the persistent grid so one CTA walks many rows / strips.
-    if (const char* ge = std::getenv("REVE_DEBUG_GRID")) {
-        const int gcap = std::atoi(ge);
-        if (gcap >= 1 && gcap < ctx->grid) ctx->grid = gcap;
-    }
-    // REVE_DEBUG_FLAGS bit0 (experiments): never sweep in reverse; bit1: CTA pairs; bit2: swap the pair's B halves.
-    ctx->pair = (dflags & 2u) != 0;
-    if (const char* pe = std::getenv("REVE_CTA_PAIRS")) ctx->pair = std::atoi(pe) != 0;   // measured: same frames/s (power-bound), see profiles/r01_notes.md
+    // Test hook: cap the persistent grid so one CTA walks many rows / strips.
+    if (opt.debug_grid >= 1 && opt.debug_grid < ctx->grid) ctx->grid = opt.debug_grid;
+    // REVE_DBG_NO_REVERSE: never sweep in reverse; REVE_DBG_CTA_PAIRS: CTA pairs (measured: same frames/s, the chip is
+    // power-bound, see profiles/r01_notes.md); REVE_DBG_SWAP_PAIR_B: swap the pair's B halves.
+    ctx->pair = (dflags & REVE_DBG_CTA_PAIRS) != 0;
     for (int k = 0; k <= kNumBody; ++k) {
         ConvParams& p = (k < kNumBody) ? ctx->body[k] : ctx->tail;
         p = ConvParams{};
@@ -614,14 +624,14 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     }
 
     ctx->chain_len = choose_chain_len(cw);
-    if (const char* ce = std::getenv("REVE_CHAIN")) {
-        const int L = std::atoi(ce);
-        if (L == 0 || L == 2 || L == 4) {
-            ctx->chain_len = L;
-            ctx->chain_forced = true;
-        }
+    if (opt.layers_per_launch) {
+        ctx->chain_len = opt.layers_per_launch == 1 ? 0 : opt.layers_per_launch;
+        ctx->chain_forced = true;
     }
+    if (opt.flags & REVE_CTX_SHARED_DEVICE) ctx->chain_len = 0;   // only kernels without inter-CTA waits
     if (ctx->pair || ctx->grid < ctx->chain_len) ctx->chain_len = 0;
+    // the chained kernel's CTAs wait for each other: it is launched cooperatively, which needs the whole grid resident
+    if (ctx->chain_len && chain_max_resident_ctas(ctx->sm_count) < (ctx->grid / ctx->chain_len) * ctx->chain_len) ctx->chain_len = 0;
     if (ctx->chain_len) {
         const int L = ctx->chain_len;
         const int P = kBoxPx - 2 * L;
@@ -658,6 +668,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
             p.reverse = (dflags & 1u) ? 0 : ((((c * L) >> 2) & 1) == 0);   // the direction of its layers (see above)
             p.flags = ctx->d_chain_flags;
             p.dbg = ctx->dbg_dev;
+            p.fault = (dflags & REVE_DBG_FAULT) ? 1u : 0u;
             for (int j = 0; j < L; ++j) {
                 const int k = c * L + j;   // body layer
                 const ConvLayer& Lr = m.conv[k + 1];
@@ -668,16 +679,15 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         }
     }
 
-    if (std::getenv("REVE_DEBUG_TRACE")) {
+    if (opt.trace) {
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_trace), 4096 * sizeof(long long)));
         CK(ctx, cudaMemset(ctx->d_trace, 0, 4096 * sizeof(long long)));
-        if (std::string(std::getenv("REVE_DEBUG_TRACE")) == "tail") ctx->tail.trace = ctx->d_trace;
-        else if (ctx->chain_len) {   // chain 0 of the second chained launch, or of launch n with REVE_DEBUG_TRACE=c<n>
-            const char* te = std::getenv("REVE_DEBUG_TRACE");
-            int idx = (te[0] == 'c') ? std::atoi(te + 1) : 1;
+        if (opt.trace == 2) ctx->tail.trace = ctx->d_trace;
+        else if (ctx->chain_len) {   // chain `trace_chain` of chained launch `trace_launch`
+            int idx = opt.trace_launch;
             if (idx < 0 || idx >= kNumBody / ctx->chain_len) idx = 1;
             ctx->chain[idx].trace = ctx->d_trace;
-            if (const char* tc = std::getenv("REVE_DEBUG_TRACE_CHAIN")) ctx->chain[idx].trace_chain = std::atoi(tc);
+            ctx->chain[idx].trace_chain = opt.trace_chain;
         }
         else ctx->body[5].trace = ctx->d_trace;
     }
@@ -729,7 +739,10 @@ int reve_device_count(int* n) {
     if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "cudaGetDeviceCount", e));
     for (int d = 0; d < ndev; ++d) {
         int major = 0;
-        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++*n;
+        int minor = -1;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10 &&
+            cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, d) == cudaSuccess && minor == 0)
+            ++*n;
     }
     return REVE_OK;
 }
@@ -823,15 +836,27 @@ void reve_model_free(reve_model* m) { delete m; }
 
 int reve_ctx_create(int device, const reve_model* m, int in_w, int in_h, int tile, int prepad, int ring_depth,
                     reve_ctx** out) {
+    return reve_ctx_create_ex(device, m, in_w, in_h, tile, prepad, ring_depth, nullptr, out);
+}
+
+int reve_ctx_create_ex(int device, const reve_model* m, int in_w, int in_h, int tile, int prepad, int ring_depth,
+                       const reve_ctx_options* opt_in, reve_ctx** out) {
     if (!out) return set_err(nullptr, REVE_E_INVAL, "out is NULL");
     *out = nullptr;
     if (!m) return set_err(nullptr, REVE_E_INVAL, "model is NULL");
+    reve_ctx_options opt = {};
+    if (opt_in) {
+        if (opt_in->struct_size < 2 * sizeof(uint32_t) || opt_in->struct_size > sizeof(reve_ctx_options))
+            return set_err(nullptr, REVE_E_INVAL, "reve_ctx_options.struct_size is not set (or from a newer header)");
+        std::memcpy(&opt, opt_in, opt_in->struct_size);
+    }
+    opt.struct_size = sizeof(reve_ctx_options);
     if (ring_depth < 1 || ring_depth > 16) return set_err(nullptr, REVE_E_INVAL, "ring_depth must be within 1..16");
     reve_ctx* ctx = new (std::nothrow) reve_ctx();
     if (!ctx) return set_err(nullptr, REVE_E_NOMEM, "out of host memory");
     int rc;
     try {
-        rc = create_ctx(ctx, device, m->m, in_w, in_h, tile, prepad, ring_depth);
+        rc = create_ctx(ctx, device, m->m, in_w, in_h, tile, prepad, ring_depth, opt);
     } catch (const std::exception& e) {
         rc = set_err(ctx, REVE_E_NOMEM, e.what());
     }
@@ -845,6 +870,32 @@ int reve_ctx_create(int device, const reve_model* m, int in_w, int in_h, int til
 }
 
 void reve_ctx_destroy(reve_ctx* ctx) { destroy_ctx(ctx); }
+
+int reve_ctx_launch_info(const reve_ctx* ctx, int* layers_per_launch, int* batch, int* grid, int* cooperative) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    const bool chained = ctx->chain_len > 1 && !ctx->chain_refused;
+    if (layers_per_launch) *layers_per_launch = chained ? ctx->chain_len : 1;
+    if (batch) *batch = ctx->batch;
+    if (grid) *grid = chained ? ctx->n_chains * ctx->chain_len : ctx->grid;
+    if (cooperative) *cooperative = chained ? 1 : 0;
+    return REVE_OK;
+}
+
+int reve_device_recover(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess && e != cudaErrorLaunchFailure) (void)cudaGetLastError();
+    if (device < 0 || (ndev > 0 && device >= ndev)) return set_err(nullptr, REVE_E_INVAL, "no such CUDA device");
+    (void)cudaSetDevice(device);     // fails on a dead context; cudaDeviceReset still tears it down
+    (void)cudaGetLastError();
+    e = cudaDeviceReset();
+    if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "cudaDeviceReset", e));
+    (void)cudaGetLastError();
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaFree(nullptr);   // re-creates the primary context
+    if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "re-initialising the device", e));
+    return REVE_OK;
+}
 
 int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale) {
     if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
@@ -1029,7 +1080,7 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
 
 int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n) {
     if (!ctx || !out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
-    if (!ctx->d_trace || n > 4096) return set_err(ctx, REVE_E_INVAL, "tracing is off (set REVE_DEBUG_TRACE=1) or n > 4096");
+    if (!ctx->d_trace || n > 4096) return set_err(ctx, REVE_E_INVAL, "tracing is off (reve_ctx_options.trace) or n > 4096");
     CK(ctx, cudaStreamSynchronize(ctx->s_comp));
     CK(ctx, cudaMemcpy(out, ctx->d_trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
     return REVE_OK;

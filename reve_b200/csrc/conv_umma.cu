@@ -893,13 +893,16 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                     const int s = seq.s, k = seq.k;
                     // one 64-bit load refreshes both streams' counters
                     bool polled = false;
-                    if ((s == 0 ? pub0 : pub1) < k) {
+                    // (test hook p.fault: chain 0's second layer waits for a row that is never announced, so that the
+                    // watchdog path -- diagnostic word, trap, REVE_E_CUDA at the ABI -- can be exercised on purpose)
+                    const int want = (p.fault && chain == 0 && j == 1) ? k + (1 << 24) : k;
+                    if ((s == 0 ? pub0 : pub1) < want) {
                         const unsigned int* const pf = p.flags + (link_in * 2 + 0) * kChainFlagStride;
                         const long long t0 = clock64();
                         do {
                             ld_acquire_gpu_v2(pf, pub0, pub1);
                             if (clock64() - t0 > (1ll << 32)) watchdog_fail(dbg, TAG_CHAIN_PUB, static_cast<uint32_t>(k), static_cast<uint32_t>(s == 0 ? pub0 : pub1));
-                        } while ((s == 0 ? pub0 : pub1) < k);
+                        } while ((s == 0 ? pub0 : pub1) < want);
                         polled = true;
                     }
                     if (polled) fence_proxy_async_global();
@@ -1153,10 +1156,35 @@ cudaError_t conv_kernels_init() {
                                 static_cast<int>(smem_bytes_t<64, false, false>()));
 }
 
+// The chained kernel's CTAs wait on each other (global-memory flags), so all of them must be resident at the same
+// time.  That is a property of the launch, not an assumption: the kernel is only ever launched cooperatively (the
+// driver starts a cooperative grid when, and only when, every CTA has its SM slot -- whatever else is running on the
+// device: a second reve_ctx, the colour-conversion kernel, an MPS co-tenant), and a grid that cannot be co-resident
+// at all is refused with cudaErrorCooperativeLaunchTooLarge instead of dead-locking.  chain_max_resident_ctas() is
+// what fits on the current device; the context falls back to single-layer launches (no inter-CTA waits) below that.
+int chain_max_resident_ctas(int sm_count) {
+    int dev = 0, coop = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv3x3_chain_kernel, kChainThreads,
+                                                      smem_bytes_t<64, false, false>()) != cudaSuccess)
+        return 0;
+    return per_sm * sm_count;
+}
+
 cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
                               const CUtensorMap& scratch_map, const ChainParams& p) {
-    conv3x3_chain_kernel<<<grid, kChainThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map, scratch_map, p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+    cfg.blockDim = dim3(kChainThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes_t<64, false, false>();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv3x3_chain_kernel, in_map, out_map, scratch_map, p);
 }
 
 cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map,

@@ -72,13 +72,16 @@ struct ChainParams {
     DebugBlock* dbg;
     long long* trace;           // debug timeline of chain `trace_chain` (device memory, may be null)
     int trace_chain;
+    uint32_t fault;             // test hook: non-zero makes chain 0 wait for a row nobody announces (watchdog path)
     const void* weights[kChainMax];
     float bias[kChainMax][64];
     __half2 slope2[kChainMax][32];
 };
 inline size_t chain_flag_words(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 2 * kChainFlagStride; }
 inline size_t chain_scratch_rows(int n_chains, int len) { return static_cast<size_t>(n_chains) * (len - 1) * 2 * kChainSlots * kBoxPx; }
-// grid = n_chains * len CTAs, all of which must be resident at the same time (one per SM)
+// grid = n_chains * len CTAs, all of which must be resident at the same time (one per SM): launched cooperatively, so
+// the driver guarantees it or refuses the launch (cudaErrorCooperativeLaunchTooLarge)
+int chain_max_resident_ctas(int sm_count);   // 0 when the device cannot launch cooperatively
 cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
                               const CUtensorMap& scratch_map, const ChainParams& p);
 

@@ -292,9 +292,17 @@ int model_load_ncnn(const std::string& param_path, const std::string& bin_path, 
     }
     if (ci_conv != kNumConv || ci_prelu != kNumConv - 1) return fail(err, REVE_E_MODEL, "layer count mismatch");
     if (off != data.size()) return fail(err, REVE_E_MODEL, bin_path + ": trailing bytes");
-    for (int k = 0; k < kNumConv; ++k)
+    // the device stores weights as fp16: an fp32-tagged payload beyond +-65504 would silently pack to +-inf
+    // (reve_model_from_arrays applies the same rule); biases and slopes stay fp32 and only need to be finite
+    for (int k = 0; k < kNumConv; ++k) {
         for (float v : m.conv[k].w)
-            if (!std::isfinite(v)) return fail(err, REVE_E_MODEL, "non-finite weight");
+            if (!std::isfinite(v) || v > 65504.f || v < -65504.f)
+                return fail(err, REVE_E_MODEL, "weight of convolution " + std::to_string(k) + " is not representable in fp16");
+        for (float v : m.conv[k].b)
+            if (!std::isfinite(v)) return fail(err, REVE_E_MODEL, "non-finite bias in convolution " + std::to_string(k));
+        for (float v : m.conv[k].slope)
+            if (!std::isfinite(v)) return fail(err, REVE_E_MODEL, "non-finite PReLU slope after convolution " + std::to_string(k));
+    }
     return REVE_OK;
 }
 

@@ -18,6 +18,9 @@ from . import _lib
 
 REVE_E_BUSY = -7
 FMT_RGB24, FMT_YUV420P10LE_BT601, FMT_YUV420P10LE_BT709 = 0, 1, 2
+CTX_SHARED_DEVICE = 1
+# test hooks (reve_ctx_options.debug_flags, include/reve_cuda.h)
+DBG_NO_REVERSE, DBG_CTA_PAIRS, DBG_SWAP_PAIR_B, DBG_ALL_ROWS, DBG_ALIAS_ROWS, DBG_FAULT = 1, 2, 4, 8, 16, 32
 
 
 class ReveError(RuntimeError):
@@ -121,15 +124,20 @@ class Model:
         return cls.from_state_dict(torch.load(path, map_location="cpu", weights_only=True), scale)
 
     @classmethod
-    def for_scale(cls, scale: int, model_dir: str = "models", seed: int = 0) -> "Model":
+    def for_scale(cls, scale: int, model_dir: str = "models", allow_random: bool = False, seed: int = 0) -> "Model":
         """The model the reference's CLI intends for ``-s scale``:
-        ``<model_dir>/realesr-animevideov3-x{scale}.param|.bin`` if present, otherwise the seeded
-        random init of the same architecture (the weight files are not available offline)."""
+        ``<model_dir>/realesr-animevideov3-x{scale}.param|.bin`` (or ``.pth``).  A missing model is an error, as it
+        is for the spawned upscaler -- a segment of noise frames with "done" lines and exit code 0 would be worse
+        than no output.  ``allow_random=True`` is the explicit opt-in (tests, benches: the weight files are not
+        available offline) for the seeded random init of the same architecture."""
         base = os.path.join(model_dir, f"realesr-animevideov3-x{scale}")
         if os.path.exists(base + ".param") and os.path.exists(base + ".bin"):
             return cls.load_ncnn(base + ".param", base + ".bin")
         if os.path.exists(base + ".pth"):
             return cls.from_pth(base + ".pth", scale)
+        if not allow_random:
+            raise ReveError(-4, f"model files {base}.param/.bin not found (model_dir is resolved against the current "
+                                f"directory, {os.getcwd()}); pass allow_random=True for random-init weights")
         return cls.random(scale, seed)
 
     def save_ncnn(self, param_path: str, bin_path: str, fp16: bool = True) -> None:
@@ -180,17 +188,34 @@ class Upscaler:
     reference's spawned upscaler uses; tile=0 is the whole-frame variant."""
 
     def __init__(self, model: Model, in_w: int, in_h: int, tile: int = 200, prepad: int = 10,
-                 device: int = 0, ring_depth: int = 3):
+                 device: int = 0, ring_depth: int = 3, *, shared_device: bool = False, layers_per_launch: int = 0,
+                 max_batch: int = 0, debug_flags: int = 0, debug_grid: int = 0, trace: int = 0, trace_launch: int = 1,
+                 trace_chain: int = 0):
+        """Keyword options map one to one onto ``reve_ctx_options`` (include/reve_cuda.h); the library reads no
+        environment variables."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.model = model
-        _check(self._lib.reve_ctx_create(device, model._h, in_w, in_h, tile, prepad, ring_depth, C.byref(self._h)))
+        opt = _lib.reve_ctx_options()
+        opt.struct_size = C.sizeof(_lib.reve_ctx_options)
+        opt.flags = CTX_SHARED_DEVICE if shared_device else 0
+        opt.layers_per_launch, opt.max_batch = layers_per_launch, max_batch
+        opt.debug_flags, opt.debug_grid = debug_flags, debug_grid
+        opt.trace, opt.trace_launch, opt.trace_chain = trace, trace_launch, trace_chain
+        _check(self._lib.reve_ctx_create_ex(device, model._h, in_w, in_h, tile, prepad, ring_depth, C.byref(opt),
+                                            C.byref(self._h)))
         v = [C.c_int() for _ in range(5)]
         _check(self._lib.reve_ctx_info(self._h, *[C.byref(x) for x in v]), self._h)
         self.in_w, self.in_h, self.out_w, self.out_h, self.scale = (x.value for x in v)
         self.ring_depth = ring_depth
         self.device = device
         self._pinned: List[int] = []
+
+    def launch_info(self) -> dict:
+        """Launch structure in use: body layers per launch, frames per launch set, CTAs, cooperative launch."""
+        v = [C.c_int() for _ in range(4)]
+        _check(self._lib.reve_ctx_launch_info(self._h, *[C.byref(x) for x in v]), self._h)
+        return {"layers_per_launch": v[0].value, "batch": v[1].value, "grid": v[2].value, "cooperative": bool(v[3].value)}
 
     # -- pinned host buffers ----------------------------------------------------------------
     def pinned(self, shape: Sequence[int]) -> np.ndarray:
@@ -354,7 +379,7 @@ def _write_frame(path: str, rgb: np.ndarray) -> None:
 
 def upscale_segment(input_dir: str, output_dir: str, scale: int, model: Optional[Model] = None,
                     tile: int = 200, prepad: int = 10, device: int = 0, fmt: str = "png",
-                    progress=None, model_dir: str = "models") -> int:
+                    progress=None, model_dir: str = "models", allow_random: bool = False) -> int:
     """Drop-in for the process spawned by Video::upscale_segment (reference
     reve-shared/src/lib.rs:134-147: ``-i input_dir -o output_dir -n realesr-animevideov3-x2 -s
     scale -f png -v``): every frame file of ``input_dir`` (sorted by name) is upscaled into
@@ -369,11 +394,14 @@ def upscale_segment(input_dir: str, output_dir: str, scale: int, model: Optional
     os.makedirs(output_dir, exist_ok=True)
     own_model = model is None
     if own_model:
-        model = Model.for_scale(scale, model_dir)
+        model = Model.for_scale(scale, model_dir, allow_random=allow_random)
     if model.scale != scale:
         raise ValueError(f"model is x{model.scale} but scale {scale} was requested")
     first = _read_frame(os.path.join(input_dir, names[0]))
     h, w = first.shape[:2]
+    # frames smaller than the pre-pad: upstream's reflect-101 reads out of bounds there (undefined); we pad as far as
+    # the rule is defined
+    prepad = min(prepad, min(w, h) - 1)
     up = Upscaler(model, w, h, tile=tile, prepad=prepad, device=device, ring_depth=3)
     try:
         ins = [up.pinned((h, w, 3)) for _ in range(up.ring_depth)]

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.reve_version() == 100
+    assert lib.reve_version() == 200
     assert lib.reve_strerror(0) == b"ok"
     assert b"sm_100" in lib.reve_strerror(-6)
     assert lib.reve_strerror(-999) == b"unknown status"
@@ -265,3 +265,57 @@ def test_launch_plan_for_the_baseline_geometries():
     assert p1["n_strips"] == 1 and p1["layers_per_launch"] == 4
     with pytest.raises(reve_b200.ReveError):
         plan(0, 10, 2)
+
+
+def test_missing_model_is_a_hard_error(lib, tmp_path):
+    """a misplaced models directory must not produce a segment of noise frames.  The reference's spawned
+    upscaler fails when models/realesr-animevideov3-x{s}.param|.bin are absent; random weights are an explicit opt-in."""
+    with pytest.raises(reve_b200.ReveError) as e:
+        reve_b200.Model.for_scale(2, str(tmp_path / "nowhere"))
+    assert e.value.status == -4 and "realesr-animevideov3-x2" in str(e.value)
+    m = reve_b200.Model.for_scale(2, str(tmp_path / "nowhere"), allow_random=True, seed=5)
+    assert m.scale == 2
+    # the segment-level mirror fails the same way, before it touches the GPU
+    np.save(str(tmp_path / "frame00000001.npy"), np.zeros((8, 8, 3), np.uint8))
+    with pytest.raises(reve_b200.ReveError) as e:
+        reve_b200.upscale_segment(str(tmp_path), str(tmp_path / "o"), 3, model_dir=str(tmp_path / "nowhere"))
+    assert e.value.status == -4
+
+
+def test_fp32_payload_outside_the_fp16_range_is_rejected(lib, tmp_path):
+    """an fp32-tagged .bin with |w| > 65504 would pack to +-inf on the device; same rule as
+    reve_model_from_arrays."""
+    w = srvgg.make_weights(2, 4, fp16_weights=False)
+    w.conv_w[5][3, 2, 1, 0] = 70000.0
+    p, b = str(tmp_path / "big.param"), str(tmp_path / "big.bin")
+    srvgg.write_ncnn(w, p, b, fp16=False)
+    with pytest.raises(reve_b200.ReveError) as e:
+        reve_b200.Model.load_ncnn(p, b)
+    assert e.value.status == -5 and "fp16" in str(e.value)
+    w.conv_w[5][3, 2, 1, 0] = 1.0
+    w.conv_b[7][0] = float("inf")
+    srvgg.write_ncnn(w, p, b, fp16=False)
+    with pytest.raises(reve_b200.ReveError) as e:
+        reve_b200.Model.load_ncnn(p, b)
+    assert e.value.status == -5
+
+
+def test_ctx_options_are_validated_before_any_device_work(lib):
+    """reve_ctx_create_ex: the options struct replaces every environment knob of round 1 (the library reads no
+    environment variables); bad values are REVE_E_INVAL, not silently ignored."""
+    m = reve_b200.Model.random(2, 1)
+    opt = _lib.reve_ctx_options()
+    h = C.c_void_p()
+    assert lib.reve_ctx_create_ex(0, m._h, 64, 64, 200, 10, 2, C.byref(opt), C.byref(h)) == -1    # struct_size unset
+    opt.struct_size = C.sizeof(_lib.reve_ctx_options)
+    opt.layers_per_launch = 3
+    assert lib.reve_ctx_create_ex(0, m._h, 64, 64, 200, 10, 2, C.byref(opt), C.byref(h)) == -1
+    assert b"layers_per_launch" in lib.reve_last_error(None)
+    opt.layers_per_launch, opt.max_batch = 0, 9
+    assert lib.reve_ctx_create_ex(0, m._h, 64, 64, 200, 10, 2, C.byref(opt), C.byref(h)) == -1
+    src = open(os.path.join(ROOT, "reve_b200", "csrc", "api.cu")).read()
+    for f in os.listdir(os.path.join(ROOT, "reve_b200", "csrc")):
+        if f.endswith((".cu", ".cpp", ".cuh", ".h")):
+            assert "getenv" not in open(os.path.join(ROOT, "reve_b200", "csrc", f)).read(), f
+    assert "cudaLaunchAttributeCooperative" in open(os.path.join(ROOT, "reve_b200", "csrc", "conv_umma.cu")).read()
+    assert src.count("launch_conv_chain(") == 1

@@ -64,16 +64,14 @@ def test_golden_vectors(path):
     (200, 150, 2, 64, None, True),    # 74 pairs, tiles
     (500, 300, 2, 200, "6", True),    # 3 pairs, streams of unequal segment counts (padding steps)
 ])
-def test_per_layer_features_and_output(w, h, scale, tile, grid, pairs, monkeypatch):
-    if grid:
-        monkeypatch.setenv("REVE_DEBUG_GRID", grid)
-    if pairs is True:
-        monkeypatch.setenv("REVE_CTA_PAIRS", "1")
-    monkeypatch.setenv("REVE_CHAIN", pairs[5:] if isinstance(pairs, str) else "0")
+def test_per_layer_features_and_output(w, h, scale, tile, grid, pairs):
+    opts = dict(debug_grid=int(grid) if grid else 0,
+                debug_flags=reve_b200.DBG_CTA_PAIRS if pairs is True else 0,
+                layers_per_launch=int(pairs[5:]) if isinstance(pairs, str) else 1)
     wts = srvgg.make_weights(scale, 1234)
     frame = srvgg.synthetic_frame(w, h, 5, "random")
     model = reve_b200.Model.random(scale, 1234)
-    with reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=2) as up:
+    with reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=2, **opts) as up:
         for layer in (1, 2, 3, 8, 9, 10, 13, 17):
             dev = up.debug_features(frame, layer)
             ref = oracle_canvas(frame, wts, tile, 10, layer)
@@ -363,19 +361,16 @@ def _random_cases(n, seed):
 
 @pytest.mark.parametrize("w,h,scale,tile,prepad,grid,pairs,chain,seed", _random_cases(36, 2026),
                          ids=lambda v: str(v))
-def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, pairs, chain, seed, monkeypatch):
+def test_random_geometries_against_the_oracle(w, h, scale, tile, prepad, grid, pairs, chain, seed):
     """Ragged sizes x tile sizes x pre-pads x scales x grid sizes x CTA pairs: every combination changes the
     stream / segment / needed-row structure the kernels walk (one row per stream, streams spanning strips,
     pre-pads shorter than the receptive field, a single CTA doing everything)."""
-    if grid:
-        monkeypatch.setenv("REVE_DEBUG_GRID", grid)
-    if pairs:
-        monkeypatch.setenv("REVE_CTA_PAIRS", "1")
-    monkeypatch.setenv("REVE_CHAIN", chain)
+    opts = dict(debug_grid=int(grid) if grid else 0, debug_flags=reve_b200.DBG_CTA_PAIRS if pairs else 0,
+                layers_per_launch=int(chain) if chain != "0" else 1)
     wts = srvgg.make_weights(scale, seed % 1000)
     model = reve_b200.Model.random(scale, seed % 1000)
     frames = [srvgg.synthetic_frame(w, h, seed + i, "random" if i % 2 else "edges") for i in range(3)]
-    with reve_b200.Upscaler(model, w, h, tile=tile, prepad=prepad, ring_depth=3) as up:
+    with reve_b200.Upscaler(model, w, h, tile=tile, prepad=prepad, ring_depth=3, **opts) as up:
         outs = [np.empty((h * scale, w * scale, 3), np.uint8) for _ in frames]
         for i, (f, o) in enumerate(zip(frames, outs)):      # three frames in flight = one stacked batch
             up.submit(f, o, i)

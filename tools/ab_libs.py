@@ -9,9 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE = r'''
 import json, os, sys
 sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(sys.path[0], "tools"))
 import torch, reve_b200
+from _opts import opts_from_env
 w, h, scale, n, frames = 1920, 1080, 2, 8, 640
-up = reve_b200.Upscaler(reve_b200.Model.random(scale, 1), w, h, tile=200, prepad=10, ring_depth=8)
+up = reve_b200.Upscaler(reve_b200.Model.random(scale, 1), w, h, tile=200, prepad=10, ring_depth=8, **opts_from_env())
 d_in = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
 d_out = torch.empty((n, h * scale, w * scale, 3), dtype=torch.uint8, device="cuda")
 st = torch.cuda.ExternalStream(up.stream)

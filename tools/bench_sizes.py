@@ -14,9 +14,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def run(w, h, scale, tile, batch, frames=64):
     import torch
     import reve_b200
+    from _opts import opts_from_env
     os.environ["REVE_DEBUG_BATCH"] = str(batch)
     model = reve_b200.Model.random(scale, 1)
-    up = reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=8)
+    up = reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=8, **opts_from_env())
     n = 8
     d_in = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
     d_out = torch.empty((n, h * scale, w * scale, 3), dtype=torch.uint8, device="cuda")

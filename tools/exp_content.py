@@ -12,8 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def run(frames_np, frames=640):
     import torch
     import reve_b200
+    from _opts import opts_from_env
     n, h, w, _ = frames_np.shape
-    up = reve_b200.Upscaler(reve_b200.Model.random(2, 1), w, h, tile=200, prepad=10, ring_depth=8)
+    up = reve_b200.Upscaler(reve_b200.Model.random(2, 1), w, h, tile=200, prepad=10, ring_depth=8, **opts_from_env())
     d_in = torch.from_numpy(frames_np).cuda()
     d_out = torch.empty((n, h * 2, w * 2, 3), dtype=torch.uint8, device="cuda")
     st = torch.cuda.ExternalStream(up.stream)

@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from helpers import feature_report, needed_rows, oracle_canvas  # noqa: E402
 from oracle import srvgg  # noqa: E402
 
+from _opts import opts_from_env  # noqa: E402
 import reve_b200  # noqa: E402
 
 
@@ -26,7 +27,7 @@ def run_case(name, w_px, h_px, scale, tile, prepad, layers, env):
     frame = srvgg.synthetic_frame(w_px, h_px, 5, "random")
     model = reve_b200.Model.random(scale, 1234)
     ok = True
-    with reve_b200.Upscaler(model, w_px, h_px, tile=tile, prepad=prepad, ring_depth=2) as up:
+    with reve_b200.Upscaler(model, w_px, h_px, tile=tile, prepad=prepad, ring_depth=2, **opts_from_env()) as up:
         for layer in layers:
             t0 = time.time()
             dev = up.debug_features(frame, layer)

@@ -9,12 +9,13 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("REVE_DEBUG_TRACE", "1")   # "c<n>": trace chained launch n
+from _opts import opts_from_env  # noqa: E402
 import reve_b200  # noqa: E402
 from reve_b200 import _lib  # noqa: E402
 
 L = int(os.environ.get("REVE_CHAIN", "4"))
 model = reve_b200.Model.random(2, 1)
-up = reve_b200.Upscaler(model, 1920, 1080, tile=200, prepad=10, ring_depth=2)
+up = reve_b200.Upscaler(model, 1920, 1080, tile=200, prepad=10, ring_depth=2, **opts_from_env())
 frame = np.random.default_rng(0).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
 for _ in range(3):
     up.upscale(frame)

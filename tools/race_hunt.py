@@ -8,6 +8,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from _opts import opts_from_env  # noqa: E402
 import reve_b200  # noqa: E402
 from oracle import srvgg  # noqa: E402
 
@@ -19,7 +20,7 @@ def main():
     model = reve_b200.Model.random(s, 11)
     frames = np.stack([srvgg.synthetic_frame(w, h, 60 + i, "random" if i % 2 else "edges") for i in range(n)])
     bad = []
-    with reve_b200.Upscaler(model, w, h, tile=200, prepad=10, ring_depth=8) as up:
+    with reve_b200.Upscaler(model, w, h, tile=200, prepad=10, ring_depth=8, **opts_from_env()) as up:
         d_in = torch.from_numpy(frames).cuda()
         ref = torch.zeros((n, h * s, w * s, 3), dtype=torch.uint8, device="cuda")
         out = torch.zeros_like(ref)
