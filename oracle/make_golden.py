@@ -44,7 +44,12 @@ CASES = [
     ("x4_tile20_real_test", ("real", "test.mp4", 300, 10, 10, 64, 48), 4, 106, 20, 10),
     ("x2_min_frame_pad10", ("random", 11, 11, 15), 2, 107, 200, 10),
     ("x3_pad0_tiny", ("random", 5, 3, 16), 3, 108, 2, 0),
+    # BASELINE.json configs[0] geometry: one whole 640x480 frame of the reference's demo asset, upstream tile 200 / pad 10
+    # (12 tiles: 3 full columns + a 40-px one, 2 full rows + an 80-px one).  Too large for the scalar C cross-check in
+    # reasonable time: pinned by the torch oracle only (the C restatement agrees on the 224x96 crop of the same frame above).
+    ("x2_tile200_real_onepiece_480p", ("real", "onepiece_demo.mp4", 60, 0, 0, 640, 480), 2, 109, 200, 10),
 ]
+NO_C_CHECK = {"x2_tile200_real_onepiece_480p"}
 
 
 def main():
@@ -56,9 +61,11 @@ def main():
             frame = srvgg.synthetic_frame(src[1], src[2], src[3], src[0])
         w = srvgg.make_weights(scale, seed)
         out = srvgg.upscale(frame, w, tile=tile, prepad=prepad)
-        out_c = cref.upscale(frame, w, tile=tile, prepad=prepad)
-        par = srvgg.parity(out, out_c)
-        assert par["within1"] == 1.0 and par["exact"] > 0.999, (name, par)
+        par = None
+        if name not in NO_C_CHECK:
+            out_c = cref.upscale(frame, w, tile=tile, prepad=prepad)
+            par = srvgg.parity(out, out_c)
+            assert par["within1"] == 1.0 and par["exact"] > 0.999, (name, par)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), frame=frame, out=out, scale=scale, seed=seed,
                             tile=tile, prepad=prepad)
         print(f"{name}: frame {frame.shape} -> {out.shape}, torch-vs-C {par}")

@@ -263,7 +263,7 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
                         const __half2 v = __floats2half2_rn(fmaf(__uint_as_float(acc[c8 * 8 + jj * 2]), 1.0f / 255.0f, p.bias[ch]),
                                                             fmaf(__uint_as_float(acc[c8 * 8 + jj * 2 + 1]), 1.0f / 255.0f, p.bias[ch + 1]));
                         const __half2 z = __float2half2_rn(0.f);
-                        const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                        const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2_nan(v, z), __hmax2_nan(v, z));
                         pk[jj] = keep ? *reinterpret_cast<const uint32_t*>(&r) : 0u;
                     }
                     st_shared_v4(stg + m * 128 + (((half * 4 + c8) ^ (m & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);

@@ -579,11 +579,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                                 const int ch = c8 * 8 + j * 2;
                                 // bias in fp32, then PReLU on the packed fp16 pair: max(v,0) + a*min(v,0).
                                 // Positive values are bit-identical to the fp32 formulation; negative ones
-                                // round twice (<= 1 ulp of fp16 instead of 0.5).
+                                // round twice (<= 1 ulp of fp16 instead of 0.5).  The _nan variants keep a NaN a
+                                // NaN (plain hmin2/hmax2 return the other operand and would turn it into 0), as
+                                // the `x < 0 ? x * slope : x` of ncnn's PReLU does; +-inf pass through either way.
                                 const __half2 v = __floats2half2_rn(__uint_as_float(acc[ch]) + p.bias[ch],
                                                                     __uint_as_float(acc[ch + 1]) + p.bias[ch + 1]);
                                 const __half2 z = __float2half2_rn(0.f);
-                                const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                                const __half2 r = __hfma2(p.slope2[ch >> 1], __hmin2_nan(v, z), __hmax2_nan(v, z));
                                 pk[j] = *reinterpret_cast<const uint32_t*>(&r);
                             }
                             st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
@@ -1071,7 +1073,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                             const __half2 v = __floats2half2_rn(__uint_as_float(acc[ch]) + bias[ch],
                                                                 __uint_as_float(acc[ch + 1]) + bias[ch + 1]);
                             const __half2 z = __float2half2_rn(0.f);
-                            const __half2 r = __hfma2(slope2[ch >> 1], __hmin2(v, z), __hmax2(v, z));
+                            const __half2 r = __hfma2(slope2[ch >> 1], __hmin2_nan(v, z), __hmax2_nan(v, z));
                             pk[jj] = *reinterpret_cast<const uint32_t*>(&r);
                         }
                         st_shared_v4(rbase + ((c8 ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);

@@ -26,7 +26,10 @@ def test_oracle_reproduces_golden(path):
     assert par["within1"] == 1.0 and par["exact"] >= 0.999, par
 
 
-@pytest.mark.parametrize("path", GOLDEN[:4], ids=[os.path.basename(p)[:-4] for p in GOLDEN[:4]])
+SMALL = [p for p in GOLDEN if os.path.getsize(p) < 100_000][:4]   # the scalar C restatement needs ~1 us per MAC
+
+
+@pytest.mark.parametrize("path", SMALL, ids=[os.path.basename(p)[:-4] for p in SMALL])
 def test_c_restatement_matches_golden(path):
     g = np.load(path)
     w = srvgg.make_weights(int(g["scale"]), int(g["seed"]))
