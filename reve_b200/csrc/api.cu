@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,6 +92,8 @@ struct reve_ctx {
     __half* d_chain_scratch = nullptr;
     unsigned int* d_chain_flags = nullptr;
     size_t chain_flag_bytes = 0;
+    float* d_chain_speed = nullptr;   // 2 x 64 floats: per-chain speed tables, swapped from chained launch to chained launch
+    unsigned chain_launches = 0;
     CUtensorMap map_chain_scratch, map_chain_out[2];
     ChainParams chain[kNumBody / 2];
     DebugBlock* dbg_host = nullptr;
@@ -253,6 +257,12 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
             c.total_rows = ctx->chain_strips * c.n_rows;
             const int chains = c.total_rows < ctx->n_chains ? c.total_rows : ctx->n_chains;
             CK(ctx, cudaMemsetAsync(ctx->d_chain_flags, 0, ctx->chain_flag_bytes, ctx->s_comp));
+            // self-balancing split (ChainParams::speed_in): full grids with enough rows per chain to measure
+            const bool balance = ctx->d_chain_speed && chains == ctx->n_chains && c.total_rows >= 256 * chains;
+            if (balance) {
+                c.speed_in = ctx->d_chain_speed + 64 * (ctx->chain_launches & 1u);
+                c.speed_out = ctx->d_chain_speed + 64 * ((ctx->chain_launches + 1u) & 1u);
+            }
             {
                 const cudaError_t le = launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, c);
                 if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
@@ -264,6 +274,7 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
                 }
                 CK(ctx, le);
             }
+            if (balance) ctx->chain_launches++;
             ctx->prof.launches_body++;
             ctx->prof.body_frames += n;
             ctx->prof.body_layer_frames += static_cast<uint64_t>(n) * L;
@@ -402,6 +413,7 @@ void destroy_ctx(reve_ctx* ctx) {
     cudaFree(ctx->d_trace);
     cudaFree(ctx->d_chain_scratch);
     cudaFree(ctx->d_chain_flags);
+    cudaFree(ctx->d_chain_speed);
     for (uint8_t* p : ctx->rgb_scratch) cudaFree(p);
     if (ctx->dbg_host) cudaFreeHost(ctx->dbg_host);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -642,6 +654,10 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         CK(ctx, cudaMemset(ctx->d_chain_scratch, 0, rows * 128));
         ctx->chain_flag_bytes = chain_flag_words(ctx->n_chains, L) * sizeof(unsigned int);
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_chain_flags), ctx->chain_flag_bytes));
+        if (!(dflags & REVE_DBG_EQUAL_SPLIT) && ctx->n_chains <= 64) {
+            const std::vector<float> ones(128, 1.0f);
+            if ((rc = upload(ctx, &ctx->d_chain_speed, ones.data(), ones.size() * sizeof(float)))) return rc;
+        }
         {
             const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
             const cuuint64_t gstride[1] = {128};
@@ -891,10 +907,17 @@ int reve_device_recover(int device) {
     e = cudaDeviceReset();
     if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "cudaDeviceReset", e));
     (void)cudaGetLastError();
-    e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaFree(nullptr);   // re-creates the primary context
-    if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "re-initialising the device", e));
-    return REVE_OK;
+    // The driver finishes tearing the faulted channel down asynchronously: until then a new primary context is refused
+    // with cudaErrorDevicesUnavailable (seen on B200, driver 580, right after a trapped kernel).  Retry for a while.
+    for (int attempt = 0;; ++attempt) {
+        e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaFree(nullptr);   // re-creates the primary context
+        if (e == cudaSuccess) return REVE_OK;
+        (void)cudaGetLastError();
+        if (attempt >= 150) break;                     // ~30 s
+        std::this_thread::sleep_for(std::chrono::milliseconds(200));
+    }
+    return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "re-initialising the device (restart the process)", e));
 }
 
 int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale) {

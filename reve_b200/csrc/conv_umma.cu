@@ -56,7 +56,13 @@ __host__ __device__ constexpr int rows_per_dx(int ng, bool pair) { return pair ?
 __host__ __device__ constexpr int w_smem_bytes(int ng, bool pair) { return 3 * rows_per_dx(ng, pair) * 128; }
 __host__ __device__ constexpr int tmem_cols(int ng) { return ng * 6 <= 128 ? 128 : (ng * 6 <= 256 ? 256 : 512); }
 // A-row ring depth: what fits next to the weights (body, one CTA: 120 KB of weights leave room for 4 rows)
-__host__ __device__ constexpr int ring_stages(int ng, bool tail, bool pair) { return (ng == 64 && !tail && !pair) ? 4 : 6; }
+// (tail x4: 92 KB of weights + the 32 KB row table leave room for 5 rows next to the output staging below)
+__host__ __device__ constexpr int ring_stages(int ng, bool tail, bool pair) { return (ng == 64 && !tail && !pair) ? 4 : ((tail && ng == 48) ? 5 : 6); }
+// Tail: per epilogue warp and output sub-row, the u8 bytes of up to 32 pixels (3*S bytes each) are gathered in shared
+// memory at the 16-byte phase of their global address, so that they leave as 16-byte vector stores (see the tail epilogue)
+__host__ __device__ constexpr int tail_scale(int ng) { return ng == 16 ? 2 : (ng == 32 ? 3 : 4); }
+__host__ __device__ constexpr int tail_row_stage(int ng) { return 16 + 32 * 3 * tail_scale(ng); }
+__host__ __device__ constexpr int tail_out_stage_bytes(int ng) { return 8 * tail_scale(ng) * tail_row_stage(ng); }
 
 // control block offsets (from the 1024-aligned base)
 constexpr int kBarW = 0;
@@ -197,6 +203,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void st_shared_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory"); }
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 // Tail: its MMAs are small (N = 3*NG <= 144), and one thread issuing for both streams leaves gaps in the tensor pipe
 // (1030 cycles per 12-MMA step); with one issuing warp per stream (warp 1: stream 0, warp 10: stream 1; the two
@@ -216,6 +235,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     constexpr int kOffRing = kOffW + kWBytes + kGuard;
     constexpr int kOffStage = kOffRing + kStages * kRowBytes + kGuard;  // body: 2 x 16 KB output staging (one per group)
     constexpr int kOffRowTab = kOffStage;                                // tail: packed row table (kTailRowTab entries)
+    constexpr int kOffOutStage = kOffRowTab + kTailRowTab * 4;           // tail: u8 output staging, [epilogue warp][sub-row]
     static_assert(kWBytes % 1024 == 0, "the A ring must stay 1024-byte aligned");
     static_assert(kStages <= kMaxStages, "ring too deep for the control block");
 
@@ -603,42 +623,77 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 }
                 if (tr) tr[3] = clock64();
             } else {
-                constexpr int S = (NG == 16) ? 2 : ((NG == 32) ? 3 : 4);
-                if (ox >= 0 && oy >= 0) {
-                    const unsigned rgb[3] = {ev.pix[0], ev.pix[1], ev.pix[2]};
-                    // S*3 consecutive bytes per output row: packed into 16-/32-bit stores when aligned
+                // u8 output: every pixel owns 3*S consecutive bytes in each of S output rows, and the valid pixels of a warp
+                // (consecutive canvas columns of one canvas row) are consecutive output pixels -- across a tile boundary too:
+                // the cropped pre-pad columns in between have ox < 0 and the kept columns of neighbouring tiles abut in the
+                // output.  So per output sub-row the warp owns ONE contiguous run of bytes.  It is assembled in shared memory
+                // at the 16-byte phase of its global address and leaves as 16-byte stores (one per lane) plus at most 15
+                // single bytes at either end, instead of 3*S (x2: 2-byte, x4: 4-byte, x3: single-byte) scattered stores per
+                // pixel and sub-row.
+                constexpr int S = tail_scale(NG);
+                constexpr int kPx = 3 * S;
+                constexpr int kRowStage = tail_row_stage(NG);
+                const bool ok = (ox >= 0) && (oy >= 0);
+                const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+                if (okmask != 0u) {
+                    const int idx = __popc(okmask & ((1u << lane) - 1u));
+                    const int tot = __popc(okmask) * kPx;
+                    const int first = __ffs(static_cast<int>(okmask)) - 1;
+                    unsigned rgb[3] = {0u, 0u, 0u};
+                    if (ok) { rgb[0] = ev.pix[0]; rgb[1] = ev.pix[1]; rgb[2] = ev.pix[2]; }
+                    uint8_t* const mine = p.dst[fr] + static_cast<long long>(oy * S) * p.dst_stride + static_cast<long long>(ox) * kPx;
+                    const unsigned long long g_first = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(mine), first);
+                    // vector stores into the staging need the run to start on a 2- (x2) / 4-byte (x4) boundary
                     const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
+                    const uint32_t wst = base + kOffOutStage + static_cast<uint32_t>(warp - 2) * (S * kRowStage);
+                    if (ok) {
 #pragma unroll
-                    for (int i = 0; i < S; ++i) {
-                        uint8_t* dp = p.dst[fr] + static_cast<long long>(oy * S + i) * p.dst_stride +
-                                      static_cast<long long>(ox) * (S * 3);
-                        uint32_t b[S * 3];
+                        for (int i = 0; i < S; ++i) {
+                            const unsigned a = static_cast<unsigned>((g_first + static_cast<unsigned long long>(i) * p.dst_stride) & 15ull);
+                            const uint32_t sp = wst + i * kRowStage + a + idx * kPx;
+                            uint32_t b[kPx];
 #pragma unroll
-                        for (int j = 0; j < S; ++j) {
+                            for (int j = 0; j < S; ++j) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const int idx = c * S * S + i * S + j;
-                                const float v = __uint_as_float(acc[idx]) +
-                                                reinterpret_cast<const float*>(base_ptr + kOffBias)[idx];
-                                // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5))
-                                float o = floorf(fmaf(v, 255.f, static_cast<float>(rgb[c]) + 0.5f));
-                                o = fminf(fmaxf(o, 0.f), 255.f);
-                                b[j * 3 + c] = static_cast<uint32_t>(o);
+                                for (int c = 0; c < 3; ++c) {
+                                    const int ch = c * S * S + i * S + j;
+                                    const float v = __uint_as_float(acc[ch]) + reinterpret_cast<const float*>(base_ptr + kOffBias)[ch];
+                                    // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5)); a NaN (overflowed fp16 activations) becomes 0
+                                    float o = floorf(fmaf(v, 255.f, static_cast<float>(rgb[c]) + 0.5f));
+                                    o = fminf(fmaxf(o, 0.f), 255.f);
+                                    b[j * 3 + c] = static_cast<uint32_t>(o);
+                                }
+                            }
+                            if (wide && S == 2) {
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) st_shared_u16(sp + 2 * k, b[2 * k] | (b[2 * k + 1] << 8));
+                            } else if (wide && S == 4) {
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    st_shared_u32(sp + 4 * k, b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24));
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < kPx; ++k) st_shared_u8(sp + k, b[k]);
                             }
                         }
-                        if (wide && S == 2) {
-                            uint16_t* d16 = reinterpret_cast<uint16_t*>(dp);   // 6*ox: 2-byte aligned
+                    }
+                    __syncwarp();
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) d16[k] = static_cast<uint16_t>(b[2 * k] | (b[2 * k + 1] << 8));
-                        } else if (wide && S == 4) {
-                            uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);   // 12*ox: 4-byte aligned
-#pragma unroll
-                            for (int k = 0; k < 3; ++k)
-                                d32[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < S * 3; ++k) dp[k] = static_cast<uint8_t>(b[k]);
+                    for (int i = 0; i < S; ++i) {
+                        const unsigned long long g = g_first + static_cast<unsigned long long>(i) * p.dst_stride;
+                        const int a = static_cast<int>(g & 15ull);
+                        uint8_t* const g0 = reinterpret_cast<uint8_t*>(g - a);            // 16-byte aligned
+                        const uint32_t sp = wst + i * kRowStage;
+                        const int end = a + tot;                                            // run = staging bytes [a, end)
+                        const int head_end = min(end, (a + 15) & ~15);                      // bytes before the first whole chunk
+                        const int tail_beg = max(end & ~15, head_end);                      // bytes after the last whole chunk
+                        const int c0 = 16 * lane;
+                        if (c0 >= head_end && c0 + 16 <= tail_beg) {
+                            const uint4 v = ld_shared_v4(sp + c0);
+                            *reinterpret_cast<uint4*>(g0 + c0) = v;
                         }
+                        if (a + lane < head_end) g0[a + lane] = static_cast<uint8_t>(ld_shared_u8(sp + a + lane));
+                        if (tail_beg + lane < end) g0[tail_beg + lane] = static_cast<uint8_t>(ld_shared_u8(sp + tail_beg + lane));
                     }
                 }
             }
@@ -784,8 +839,23 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     long long lo[2], hi[2];
     {
         const unsigned b = rev ? (n_chains - 1 - chain) : chain;
-        const long long wlo = static_cast<long long>(b) * p.total_rows / n_chains;
-        const long long whi = static_cast<long long>(b + 1) * p.total_rows / n_chains;
+        long long wlo = static_cast<long long>(b) * p.total_rows / n_chains;
+        long long whi = static_cast<long long>(b + 1) * p.total_rows / n_chains;
+        if (p.speed_in) {
+            // block position q is worked by chain q (forward) or n_chains-1-q (reverse); every CTA runs the same
+            // additions in the same order, so neighbouring chains agree on their common boundary to the bit
+            float sum = 0.f, below = 0.f, upto = 0.f;
+            for (unsigned q = 0; q < n_chains; ++q) {
+                float wq = p.speed_in[rev ? n_chains - 1 - q : q];
+                if (!(wq > 0.25f && wq < 4.f)) wq = 1.f;
+                if (q == b) below = sum;
+                sum += wq;
+                if (q == b) upto = sum;
+            }
+            wlo = static_cast<long long>(static_cast<double>(p.total_rows) * static_cast<double>(below) / static_cast<double>(sum));
+            whi = (b + 1 == n_chains) ? static_cast<long long>(p.total_rows)
+                                      : static_cast<long long>(static_cast<double>(p.total_rows) * static_cast<double>(upto) / static_cast<double>(sum));
+        }
         lo[0] = wlo;
         hi[0] = lo[1] = wlo + (whi - wlo) / 2;
         hi[1] = whi;
@@ -947,6 +1017,8 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         uint32_t i = 0;
         long long* const cta_tr = (p.trace && lane == 0) ? p.trace + 2048 + blockIdx.x * 4 : nullptr;   // per-CTA: ns
         if (cta_tr) cta_tr[0] = static_cast<long long>(globaltimer_ns());
+        const bool clocked = last && p.speed_out != nullptr;     // the chain's last layer times the chain (see ChainParams)
+        unsigned long long t_first = 0;
         bool have = seq.next();
         if (have) {
             const Gate g = gate_of(0, seq.s, seq.k);
@@ -954,6 +1026,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             tc_fence_after();
         }
         if (cta_tr) cta_tr[1] = static_cast<long long>(globaltimer_ns());
+        if (clocked) t_first = globaltimer_ns();
         const bool elected = elect_one();
         while (have) {
             const int s = seq.s, k = seq.k;
@@ -997,6 +1070,20 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             cta_tr[3] = static_cast<long long>(i) | (static_cast<long long>(smid) << 32);
+        }
+        if (clocked && lane == 0) {
+            // steps per microsecond of this chain (its slowest layer paces the last one), averaged with the figure the
+            // split of this launch was based on; short launches carry no information and hand the old figure on
+            float old = p.speed_in ? p.speed_in[chain] : 1.f;
+            if (!(old > 0.25f && old < 4.f)) old = 1.f;
+            const unsigned long long dt = globaltimer_ns() - t_first;
+            float now = old;
+            if (i >= 256u && dt > 0ull) {
+                now = 1000.f * static_cast<float>(i) / static_cast<float>(dt);
+                now = fminf(fmaxf(now, 0.5f), 2.5f);
+                if (p.speed_in && old != 1.f) now = 0.5f * (old + now);
+            }
+            p.speed_out[chain] = now;
         }
         __syncwarp();
     } else {
@@ -1112,7 +1199,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
 template <int NG, bool TAIL, bool PAIR>
 constexpr size_t smem_bytes_t() {
     return 1024 /*alignment slack*/ + kCtrlBytes + w_smem_bytes(NG, PAIR) + kGuard +
-           ring_stages(NG, TAIL, PAIR) * kRowBytes + kGuard + (TAIL ? kTailRowTab * 4 : 2 * kRowBytes);
+           ring_stages(NG, TAIL, PAIR) * kRowBytes + kGuard + (TAIL ? kTailRowTab * 4 + tail_out_stage_bytes(NG) : 2 * kRowBytes);
 }
 
 template <int NG, bool TAIL, bool PAIR>

@@ -73,6 +73,13 @@ struct ChainParams {
     long long* trace;           // debug timeline of chain `trace_chain` (device memory, may be null)
     int trace_chain;
     uint32_t fault;             // test hook: non-zero makes chain 0 wait for a row nobody announces (watchdog path)
+    // Self-balancing split of the strip-rows over the chains: chains run at different speeds (their SMs sit at different
+    // distances from the L2 slices that hold the hand-over rings: 841..930 ns per step measured), and a launch ends with
+    // its slowest chain.  speed_in[c] = steps per microsecond chain c sustained in the previous chained launch (written by
+    // that launch into ITS speed_out; two tables, swapped by the host from launch to launch), and the block of chain c is
+    // sized in proportion.  Null = equal blocks.  The split moves work between chains, never the arithmetic of a pixel.
+    const float* speed_in;
+    float* speed_out;
     const void* weights[kChainMax];
     float bias[kChainMax][64];
     __half2 slope2[kChainMax][32];

@@ -536,10 +536,13 @@ def test_fp16_range_stress_large_activations():
 
 
 def test_fp16_overflow_saturates_like_the_oracle():
-    """Activations beyond 65504 become +-inf when stored as fp16 (device and oracle's fp16_storage path alike), and
-    inf - inf in the next convolution is NaN.  Pinned here: the CLASS of every feature value (finite / +inf / -inf / NaN)
-    after layers 1 and 2 agrees with the oracle, PReLU keeps NaN a NaN (as ncnn's `x < 0 ? x * slope : x`), the final
-    quantiser maps NaN to 0 and +-inf to 255 / 0 (oracle/srvgg.py:quantise), and nothing traps."""
+    """Convolution results beyond +-65504 become +-inf when rounded to fp16, and inf - inf in the next convolution is
+    NaN.  Pinned here against the oracle's fp16-arithmetic variant (oracle/srvgg.py:forward, fp16_storage="arith": round
+    the convolution result to fp16, then PReLU on fp16 operands -- ncnn's fp16 path and the device's): the CLASS of every
+    feature value (finite / +inf / -inf / NaN) after layers 1 and 2 agrees, PReLU keeps NaN a NaN (ncnn:
+    `x < 0 ? x * slope : x`), the final quantiser maps NaN to 0 and +-inf to 255 / 0 (oracle/srvgg.py:quantise), and
+    nothing traps.  (The fp16-STORAGE variant -- PReLU in fp32, then round -- keeps values in (-65504/slope, -65504)
+    finite; upstream's CPU and fp16-Vulkan paths differ in exactly this way, it only matters once a model overflows.)"""
     scale = 2
     wts = _scaled_weights(scale, 78, 4.0e4)      # conv0 weights stay below 65504, its outputs (std ~3e4) do not
     frame = srvgg.synthetic_frame(200, 120, 10, "random")
@@ -549,14 +552,14 @@ def test_fp16_overflow_saturates_like_the_oracle():
         again = up.upscale(frame)
     assert np.array_equal(out, again)
     x = (srvgg.padded_tile(frame, 0, 0, 200, 120, 10).astype(np.float32) * np.float32(1 / 255.0)).transpose(2, 0, 1)
-    y16, ref16, _ = srvgg.forward(x, wts, taps=True, fp16_storage=True)
+    y16, ref16, _ = srvgg.forward(x, wts, taps=True, fp16_storage="arith")
 
     def classes(a):
         return np.where(np.isnan(a), 3, np.where(np.isposinf(a), 1, np.where(np.isneginf(a), 2, 0)))
 
     c1, r1 = classes(f1), classes(ref16[0].transpose(1, 2, 0))
     c2, r2 = classes(f2), classes(ref16[1].transpose(1, 2, 0))
-    assert (r1 == 1).mean() > 0.01 and (r2 == 3).mean() > 0.01          # the case does overflow, and does produce NaN
+    assert (r1 == 1).mean() > 0.01 and (r1 == 2).mean() > 0.005 and (r2 == 3).mean() > 0.01   # overflows both ways, and NaN
     # values within one fp16 ulp of the overflow threshold may fall on either side (fp32 summation order)
     assert (c1 == r1).mean() >= 0.999, float((c1 == r1).mean())
     assert (c2 == r2).mean() >= 0.995, float((c2 == r2).mean())
