@@ -129,12 +129,15 @@ int reve_ctx_launch_info(const reve_ctx* ctx, int* layers_per_launch, int* batch
  * with a trap after writing a diagnostic word to host-mapped memory; the call that notices it (reve_wait, reve_sync,
  * reve_submit, ...) returns REVE_E_CUDA and reve_last_error(ctx) carries "kernel watchdog: wait tag T timed out in
  * block B".  As after any asynchronous CUDA fault (Xid, ECC, illegal address) the error is STICKY: the CUDA primary
- * context of that device is lost for the whole process, so every reve_ctx on the same device fails from then on
- * (contexts on other devices are unaffected) and the frames in flight are lost.  Recovery without restarting the
- * process: reve_ctx_destroy every context of that device (safe on a dead context), drop -- do not free -- the pinned
- * buffers obtained from reve_host_alloc while that device was current, call reve_device_recover(device), then create
- * contexts again and resubmit from the last frame whose reve_wait succeeded.  reve_model handles live in host memory
- * and stay valid. */
+ * context of that device is lost for the whole process, so every reve_ctx on the same device fails with REVE_E_CUDA
+ * from then on (contexts on other devices and other processes are unaffected) and the frames in flight are lost;
+ * reve_ctx_destroy stays safe on a dead context.  What a caller should do: destroy the contexts of that device, record
+ * the last frame whose reve_wait succeeded, and restart the worker PROCESS for that device (the segment scheduler's
+ * resume file makes that cheap: an unfinished segment is simply still listed).  reve_device_recover(device) attempts
+ * the in-process alternative -- cudaDeviceReset and a fresh primary context, after which contexts can be created
+ * again (pinned buffers obtained while that device was current must be dropped, not freed; reve_model handles live
+ * in host memory and stay valid) -- but whether the driver allows it is not ours to decide: on the B200 / driver 580
+ * pool this library was developed on it is refused (cudaErrorDevicesUnavailable, returned as REVE_E_CUDA). */
 int reve_device_recover(int device);
 /* Geometry of the context: output frame size and scale. */
 int reve_ctx_info(const reve_ctx* ctx, int* in_w, int* in_h, int* out_w, int* out_h, int* scale);
@@ -207,6 +210,16 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
  * epilogue group 0: out[1024 + 4*e + 0..3] = wait start / accumulator full / slot released / row stored of
  * event e); this copies the first n (<= 2048) words out.  See tools/gpu_trace.py. */
 int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n);
+/* Test hooks for the stand-alone conversion kernels (reve_b200/csrc/pack.cu; SURVEY.md section 2.3 K1 / K7 -- the
+ * product path fuses both conversions into conv0 and the tail).  One frame of the context's geometry.
+ * unpack: u8 RGB frame -> x/255 as fp16 on the canvas (reflect-101 pre-pad, zero gaps), returned as float32
+ *         [canvas_h][canvas_w][3].
+ * pack:   `y` = float32 [canvas_h*s][canvas_w*s][3], a network output at canvas geometry (rounded to fp16 on upload)
+ *         -> cropped u8 RGB frame, u8 = clamp(floor(v*255 + 0.5)).
+ * ms (may be NULL): device time of the kernel alone, average of `reps` launches (CUDA events). */
+int reve_debug_unpack(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, float* out, size_t cap_floats, int reps, float* ms);
+int reve_debug_pack(reve_ctx* ctx, const float* y, size_t n_floats, uint8_t* rgb_out, size_t out_stride, int reps, float* ms);
+
 /* Canvas geometry tables (context-free, host only; test hook): the canvas is the side-by-side
  * layout of upstream's padded tiles.  For canvas column/row i: the source frame coordinate feeding
  * it (reflect-101 applied; -1 for a gap) and the output coordinate at input resolution (-1 if

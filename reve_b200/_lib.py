@@ -57,6 +57,8 @@ SIGNATURES = {
     "reve_debug_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "reve_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "reve_debug_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
+    "reve_debug_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "reve_geometry": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 2 + [C.c_void_p] * 4 + [C.c_size_t]),
     "reve_launch_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 4),
 }

@@ -92,8 +92,10 @@ struct reve_ctx {
     __half* d_chain_scratch = nullptr;
     unsigned int* d_chain_flags = nullptr;
     size_t chain_flag_bytes = 0;
-    float* d_chain_speed = nullptr;   // 2 x 64 floats: per-chain speed tables, swapped from chained launch to chained launch
-    unsigned chain_launches = 0;
+    // per-chain speed tables of the self-balancing split: one pair per chained launch of the frame (the launches differ in
+    // sweep direction and needed rows, i.e. in which part of the canvas a chain works on), swapped every time it runs
+    float* d_chain_speed = nullptr;   // [kNumBody / 2][2][64] floats
+    unsigned chain_launches[kNumBody / 2] = {};
     CUtensorMap map_chain_scratch, map_chain_out[2];
     ChainParams chain[kNumBody / 2];
     DebugBlock* dbg_host = nullptr;
@@ -260,8 +262,9 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
             // self-balancing split (ChainParams::speed_in): full grids with enough rows per chain to measure
             const bool balance = ctx->d_chain_speed && chains == ctx->n_chains && c.total_rows >= 256 * chains;
             if (balance) {
-                c.speed_in = ctx->d_chain_speed + 64 * (ctx->chain_launches & 1u);
-                c.speed_out = ctx->d_chain_speed + 64 * ((ctx->chain_launches + 1u) & 1u);
+                float* const pair = ctx->d_chain_speed + 128 * (k / L);
+                c.speed_in = pair + 64 * (ctx->chain_launches[k / L] & 1u);
+                c.speed_out = pair + 64 * ((ctx->chain_launches[k / L] + 1u) & 1u);
             }
             {
                 const cudaError_t le = launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, c);
@@ -274,7 +277,7 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
                 }
                 CK(ctx, le);
             }
-            if (balance) ctx->chain_launches++;
+            if (balance) ctx->chain_launches[k / L]++;
             ctx->prof.launches_body++;
             ctx->prof.body_frames += n;
             ctx->prof.body_layer_frames += static_cast<uint64_t>(n) * L;
@@ -655,7 +658,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         ctx->chain_flag_bytes = chain_flag_words(ctx->n_chains, L) * sizeof(unsigned int);
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_chain_flags), ctx->chain_flag_bytes));
         if (!(dflags & REVE_DBG_EQUAL_SPLIT) && ctx->n_chains <= 64) {
-            const std::vector<float> ones(128, 1.0f);
+            const std::vector<float> ones(128 * (kNumBody / 2), 1.0f);
             if ((rc = upload(ctx, &ctx->d_chain_speed, ones.data(), ones.size() * sizeof(float)))) return rc;
         }
         {
@@ -907,14 +910,16 @@ int reve_device_recover(int device) {
     e = cudaDeviceReset();
     if (e != cudaSuccess) return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "cudaDeviceReset", e));
     (void)cudaGetLastError();
-    // The driver finishes tearing the faulted channel down asynchronously: until then a new primary context is refused
-    // with cudaErrorDevicesUnavailable (seen on B200, driver 580, right after a trapped kernel).  Retry for a while.
+    // Whether a process may build a new primary context after a faulted one is the driver's decision: on the B200 pool
+    // this was developed on (driver 580) it is refused with cudaErrorDevicesUnavailable for as long as the process lives
+    // (retried for 30 s), so the only recovery there is a new process.  A few retries cover drivers that merely need a
+    // moment to tear the faulted channel down.
     for (int attempt = 0;; ++attempt) {
         e = cudaSetDevice(device);
         if (e == cudaSuccess) e = cudaFree(nullptr);   // re-creates the primary context
         if (e == cudaSuccess) return REVE_OK;
         (void)cudaGetLastError();
-        if (attempt >= 150) break;                     // ~30 s
+        if (attempt >= 15) break;                      // ~3 s
         std::this_thread::sleep_for(std::chrono::milliseconds(200));
     }
     return set_err(nullptr, REVE_E_CUDA, cuda_msg(nullptr, "re-initialising the device (restart the process)", e));
@@ -1099,6 +1104,93 @@ int reve_debug_features(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, 
         out[i] = f16_to_f32(bits);
     }
     return REVE_OK;
+}
+
+}  // extern "C" (templates cannot have C linkage)
+namespace {
+// average device time of `reps` launches of fn on the compute stream
+template <typename F>
+int timed_launches(reve_ctx* ctx, int reps, float* ms, F fn) {
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    CK(ctx, fn());                                    // warm-up (and the result the caller reads)
+    CK(ctx, cudaEventRecord(e0, ctx->s_comp));
+    for (int r = 0; r < reps; ++r) CK(ctx, fn());
+    CK(ctx, cudaEventRecord(e1, ctx->s_comp));
+    CK(ctx, cudaStreamSynchronize(ctx->s_comp));
+    float t = 0.f;
+    CK(ctx, cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = reps > 0 ? t / reps : 0.f;
+    return REVE_OK;
+}
+}  // namespace
+extern "C" {
+
+int reve_debug_unpack(reve_ctx* ctx, const uint8_t* rgb_in, size_t in_stride, float* out, size_t cap_floats, int reps, float* ms) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    const int cw = ctx->g.canvas_w(), ch = ctx->g.canvas_h();
+    const size_t px = static_cast<size_t>(cw) * ch;
+    const size_t in_row = static_cast<size_t>(ctx->g.in_w) * 3;
+    if (!rgb_in || !out || in_stride < in_row || cap_floats < px * 3 || reps < 0) return set_err(ctx, REVE_E_INVAL, "bad argument");
+    if (ctx->inflight) return set_err(ctx, REVE_E_BUSY, "frames in flight");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->ring[0];
+    CK(ctx, cudaMemcpy2DAsync(s.d_in, in_row, rgb_in, in_stride, in_row, ctx->g.in_h, cudaMemcpyHostToDevice, ctx->s_comp));
+    void* d = nullptr;
+    CK(ctx, cudaMalloc(&d, px * 8));
+    // the y table of a single frame: the first canvas_h entries of the stacked table
+    int rc = timed_launches(ctx, reps, ms, [&] {
+        return launch_unpack_rgb8(ctx->s_comp, s.d_in, static_cast<long long>(in_row), ctx->d_srcx, ctx->d_srcy, cw, ch, d);
+    });
+    std::vector<uint16_t> h(px * 4);
+    if (rc == REVE_OK && cudaMemcpy(h.data(), d, px * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_err(ctx, REVE_E_CUDA, "copy back failed");
+    cudaFree(d);
+    if (rc != REVE_OK) return rc;
+    for (size_t i = 0; i < px; ++i)
+        for (int c = 0; c < 3; ++c) out[i * 3 + c] = f16_to_f32(h[i * 4 + c]);
+    return REVE_OK;
+}
+
+int reve_debug_pack(reve_ctx* ctx, const float* y, size_t n_floats, uint8_t* rgb_out, size_t out_stride, int reps, float* ms) {
+    if (!ctx) return set_err(nullptr, REVE_E_INVAL, "ctx is NULL");
+    const int cw = ctx->g.canvas_w(), ch = ctx->g.canvas_h(), sc = ctx->scale;
+    const size_t px = static_cast<size_t>(cw) * sc * ch * sc;
+    const int out_w = ctx->g.in_w * sc, out_h = ctx->g.in_h * sc;
+    if (!y || !rgb_out || n_floats != px * 3 || out_stride < static_cast<size_t>(out_w) * 3 || reps < 0) return set_err(ctx, REVE_E_INVAL, "bad argument");
+    if (ctx->inflight) return set_err(ctx, REVE_E_BUSY, "frames in flight");
+    CK(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint16_t> h(px * 4, 0);
+    for (size_t i = 0; i < px; ++i)
+        for (int c = 0; c < 3; ++c) h[i * 4 + c] = f32_to_f16(y[i * 3 + c]);
+    // output -> canvas tables at input resolution (every output coordinate is kept by exactly one canvas coordinate)
+    std::vector<int> inv_x(ctx->g.in_w, -1), inv_y(ctx->g.in_h, -1);
+    for (int i = 0; i < cw; ++i) if (ctx->g.x.out[i] >= 0) inv_x[ctx->g.x.out[i]] = i;
+    for (int i = 0; i < ch; ++i) if (ctx->g.y.out[i] >= 0) inv_y[ctx->g.y.out[i]] = i;
+    void* d = nullptr;
+    int *dx = nullptr, *dy = nullptr;
+    int rc = REVE_OK;
+    if (cudaMalloc(&d, px * 8) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&dx), inv_x.size() * 4) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&dy), inv_y.size() * 4) != cudaSuccess)
+        rc = set_err(ctx, REVE_E_NOMEM, "out of device memory");
+    if (rc == REVE_OK && (cudaMemcpy(d, h.data(), px * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+                          cudaMemcpy(dx, inv_x.data(), inv_x.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                          cudaMemcpy(dy, inv_y.data(), inv_y.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess))
+        rc = set_err(ctx, REVE_E_CUDA, "upload failed");
+    Slot& s = ctx->ring[0];
+    const size_t out_row = static_cast<size_t>(out_w) * 3;
+    if (rc == REVE_OK)
+        rc = timed_launches(ctx, reps, ms, [&] {
+            return launch_pack_rgb8(ctx->s_comp, d, cw, sc, dx, dy, out_w, out_h, s.d_out, static_cast<long long>(out_row));
+        });
+    if (rc == REVE_OK && cudaMemcpy2D(rgb_out, out_stride, s.d_out, out_row, out_row, out_h, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = set_err(ctx, REVE_E_CUDA, "copy back failed");
+    cudaFree(d);
+    cudaFree(dx);
+    cudaFree(dy);
+    return rc;
 }
 
 int reve_debug_trace(reve_ctx* ctx, long long* out, size_t n) {

@@ -60,6 +60,10 @@ __host__ __device__ constexpr int tmem_cols(int ng) { return ng * 6 <= 128 ? 128
 __host__ __device__ constexpr int ring_stages(int ng, bool tail, bool pair) { return (ng == 64 && !tail && !pair) ? 4 : ((tail && ng == 48) ? 5 : 6); }
 // Tail: per epilogue warp and output sub-row, the u8 bytes of up to 32 pixels (3*S bytes each) are gathered in shared
 // memory at the 16-byte phase of their global address, so that they leave as 16-byte vector stores (see the tail epilogue)
+#ifndef REVE_TAIL_STAGED_MASK
+#define REVE_TAIL_STAGED_MASK 8      // bit S set: scale S writes its u8 output through the shared-memory staging (x3 only)
+#endif
+constexpr int kTailStagedMask = REVE_TAIL_STAGED_MASK;
 __host__ __device__ constexpr int tail_scale(int ng) { return ng == 16 ? 2 : (ng == 32 ? 3 : 4); }
 __host__ __device__ constexpr int tail_row_stage(int ng) { return 16 + 32 * 3 * tail_scale(ng); }
 __host__ __device__ constexpr int tail_out_stage_bytes(int ng) { return 8 * tail_scale(ng) * tail_row_stage(ng); }
@@ -623,16 +627,57 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 }
                 if (tr) tr[3] = clock64();
             } else {
-                // u8 output: every pixel owns 3*S consecutive bytes in each of S output rows, and the valid pixels of a warp
-                // (consecutive canvas columns of one canvas row) are consecutive output pixels -- across a tile boundary too:
-                // the cropped pre-pad columns in between have ox < 0 and the kept columns of neighbouring tiles abut in the
-                // output.  So per output sub-row the warp owns ONE contiguous run of bytes.  It is assembled in shared memory
-                // at the 16-byte phase of its global address and leaves as 16-byte stores (one per lane) plus at most 15
-                // single bytes at either end, instead of 3*S (x2: 2-byte, x4: 4-byte, x3: single-byte) scattered stores per
-                // pixel and sub-row.
+                // u8 output: every pixel owns 3*S consecutive bytes in each of S output rows.  Two ways to write them:
+                //  * direct: 3*S/2 two-byte (x2), 3*S/4 four-byte (x4) or 3*S single-byte (x3) stores per pixel and sub-row;
+                //    neighbouring lanes write neighbouring pixels, so a warp-wide store instruction covers one contiguous
+                //    span (192 / 288 / 384 bytes) with interleaved pieces that L2 merges;
+                //  * staged (kTailStagedMask, bit S): the valid pixels of a warp (consecutive canvas columns of one canvas
+                //    row) are consecutive output pixels -- across a tile boundary too: the cropped pre-pad columns in
+                //    between have ox < 0 and the kept columns of neighbouring tiles abut in the output.  So per output
+                //    sub-row the warp owns ONE contiguous run of bytes; it is assembled in shared memory at the 16-byte
+                //    phase of its global address and leaves as 16-byte stores (one per lane) plus at most 15 single bytes
+                //    at either end.
+                // Which one a scale uses is decided by measurement (profiles/r02_notes.md): the tail's epilogue is its
+                // critical resource, and the extra shared-memory round trip has to pay for itself.
                 constexpr int S = tail_scale(NG);
                 constexpr int kPx = 3 * S;
                 constexpr int kRowStage = tail_row_stage(NG);
+                if constexpr (((kTailStagedMask >> S) & 1) == 0) {
+                if (ox >= 0 && oy >= 0) {
+                    const unsigned rgb[3] = {ev.pix[0], ev.pix[1], ev.pix[2]};
+                    const bool wide = (S != 3) && (((reinterpret_cast<uintptr_t>(p.dst[fr]) | static_cast<uintptr_t>(p.dst_stride)) & 3) == 0);
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        uint8_t* dp = p.dst[fr] + static_cast<long long>(oy * S + i) * p.dst_stride + static_cast<long long>(ox) * kPx;
+                        uint32_t b[kPx];
+#pragma unroll
+                        for (int j = 0; j < S; ++j) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int ch = c * S * S + i * S + j;
+                                const float v = __uint_as_float(acc[ch]) + reinterpret_cast<const float*>(base_ptr + kOffBias)[ch];
+                                // y = r + x/255 ; u8 = clamp(floor(y*255 + 0.5)); a NaN (overflowed fp16 activations) becomes 0
+                                float o = floorf(fmaf(v, 255.f, static_cast<float>(rgb[c]) + 0.5f));
+                                o = fminf(fmaxf(o, 0.f), 255.f);
+                                b[j * 3 + c] = static_cast<uint32_t>(o);
+                            }
+                        }
+                        if (wide && S == 2) {
+                            uint16_t* d16 = reinterpret_cast<uint16_t*>(dp);   // 6*ox: 2-byte aligned
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) d16[k] = static_cast<uint16_t>(b[2 * k] | (b[2 * k + 1] << 8));
+                        } else if (wide && S == 4) {
+                            uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);   // 12*ox: 4-byte aligned
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                d32[k] = b[4 * k] | (b[4 * k + 1] << 8) | (b[4 * k + 2] << 16) | (b[4 * k + 3] << 24);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kPx; ++k) dp[k] = static_cast<uint8_t>(b[k]);
+                        }
+                    }
+                }
+                } else {
                 const bool ok = (ox >= 0) && (oy >= 0);
                 const unsigned okmask = __ballot_sync(0xffffffffu, ok);
                 if (okmask != 0u) {
@@ -696,6 +741,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         if (tail_beg + lane < end) g0[tail_beg + lane] = static_cast<uint8_t>(ld_shared_u8(sp + tail_beg + lane));
                     }
                 }
+                }   // staged
             }
         }
     }

@@ -126,6 +126,14 @@ YuvCoeffs colour_coeffs(int matrix);
 cudaError_t launch_rgb_to_yuv420p10(cudaStream_t st, const uint8_t* rgb, long long rgb_stride, int w, int h,
                                     uint16_t* y, long long y_stride, uint16_t* u, uint16_t* v, long long c_stride,
                                     const YuvCoeffs& c);
+// Stand-alone u8 RGB <-> fp16 conversions (pack.cu; the product path fuses both, these exist for tests and measurement).
+// unpack: u8 RGB frame -> fp16 RGB0 canvas [ch][cw] (x / 255, reflect-101 pre-pad and gaps through the geometry tables)
+cudaError_t launch_unpack_rgb8(cudaStream_t st, const uint8_t* src, long long src_stride, const int* src_x, const int* src_y,
+                               int cw, int ch, void* dst_rgb0_f16);
+// pack: fp16 RGB0 network output at canvas geometry [ch*s][cw*s] -> cropped u8 RGB frame, u8 = clamp(floor(v*255 + 0.5));
+// inv_x / inv_y: output column / row at input resolution -> canvas column / row
+cudaError_t launch_pack_rgb8(cudaStream_t st, const void* src_rgb0_f16, int cw, int scale, const int* inv_x, const int* inv_y,
+                             int out_w, int out_h, uint8_t* dst, long long dst_stride);
 size_t conv0_weight_blob_bytes();
 void pack_conv0_weights(const float* w_oihw, uint16_t* blob);
 cudaError_t conv0_kernel_init();

@@ -334,6 +334,26 @@ class Upscaler:
                                              out.ctypes.data, out.size, C.byref(cw), C.byref(ch)), self._h)
         return out
 
+    # -- stand-alone conversion kernels (pack.cu; test / measurement hooks) ------------------------------------
+    def debug_unpack(self, frame: np.ndarray, reps: int = 0):
+        """u8 frame -> (x/255 as fp16 on the canvas, returned float32 [CH, CW, 3]; kernel ms averaged over reps)."""
+        frame = np.ascontiguousarray(frame)
+        cw, ch = C.c_int(), C.c_int()
+        self._lib.reve_debug_features(self._h, None, 0, 0, None, 0, C.byref(cw), C.byref(ch))
+        out = np.empty((ch.value, cw.value, 3), np.float32)
+        ms = C.c_float()
+        _check(self._lib.reve_debug_unpack(self._h, frame.ctypes.data, frame.strides[0], out.ctypes.data, out.size, reps,
+                                           C.byref(ms)), self._h)
+        return out, ms.value
+
+    def debug_pack(self, y: np.ndarray, reps: int = 0):
+        """float32 [CH*s, CW*s, 3] network output at canvas geometry -> (cropped u8 frame [H*s, W*s, 3], kernel ms)."""
+        y = np.ascontiguousarray(y, np.float32)
+        out = np.empty((self.out_h, self.out_w, 3), np.uint8)
+        ms = C.c_float()
+        _check(self._lib.reve_debug_pack(self._h, y.ctypes.data, y.size, out.ctypes.data, out.strides[0], reps, C.byref(ms)), self._h)
+        return out, ms.value
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.reve_ctx_destroy(self._h)
