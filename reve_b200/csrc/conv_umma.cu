@@ -61,7 +61,10 @@ __host__ __device__ constexpr int ring_stages(int ng, bool tail, bool pair) { re
 // Tail: per epilogue warp and output sub-row, the u8 bytes of up to 32 pixels (3*S bytes each) are gathered in shared
 // memory at the 16-byte phase of their global address, so that they leave as 16-byte vector stores (see the tail epilogue)
 #ifndef REVE_TAIL_STAGED_MASK
-#define REVE_TAIL_STAGED_MASK 8      // bit S set: scale S writes its u8 output through the shared-memory staging (x3 only)
+// bit S set: scale S writes its u8 output through the shared-memory staging.  Default: none.  Same-box A/B on B200
+// (profiles/r02_ab_tail_output_path.txt, ms per frame, direct vs staged): x2 1080p 0.098 vs 0.121, x3 540p 0.0430 vs
+// 0.0443, x4 720p 0.0822 vs 0.0958 -- the direct stores win at every scale, see the tail epilogue.
+#define REVE_TAIL_STAGED_MASK 0
 #endif
 constexpr int kTailStagedMask = REVE_TAIL_STAGED_MASK;
 __host__ __device__ constexpr int tail_scale(int ng) { return ng == 16 ? 2 : (ng == 32 ? 3 : 4); }
@@ -637,8 +640,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 //    sub-row the warp owns ONE contiguous run of bytes; it is assembled in shared memory at the 16-byte
                 //    phase of its global address and leaves as 16-byte stores (one per lane) plus at most 15 single bytes
                 //    at either end.
-                // Which one a scale uses is decided by measurement (profiles/r02_notes.md): the tail's epilogue is its
-                // critical resource, and the extra shared-memory round trip has to pay for itself.
+                // Measured on B200 (REVE_TAIL_STAGED_MASK above): the staged path is slower at every scale, by 24 % (x2), 3 %
+                // (x3) and 17 % (x4) of the tail kernel.  The tail's epilogue warps are its critical resource (DESIGN.md
+                // section 4.2): the ballot / shuffle / shared-memory round trip adds more instructions to them than the
+                // narrow stores cost, and L2 merges the pieces of a warp-wide store into full sectors anyway (the output
+                // is 1/13 of the kernel's traffic).  The direct path is what ships; the staged one stays selectable.
                 constexpr int S = tail_scale(NG);
                 constexpr int kPx = 3 * S;
                 constexpr int kRowStage = tail_row_stage(NG);
@@ -810,6 +816,9 @@ struct ChainCursor {
     }
 };
 
+#ifndef REVE_CONSUMED_RELEASE
+#define REVE_CONSUMED_RELEASE 0
+#endif
 #ifndef REVE_PUBLISH_EVERY
 #define REVE_PUBLISH_EVERY 2
 #endif
@@ -1004,8 +1013,15 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                     if (i >= 2) {   // the load issued two steps ago has landed: its scratch slot may be overwritten
                         const uint32_t o = i - 2;
                         mbar_wait(base + kBarAFull + 8 * (o % kStages), (o / kStages) & 1, dbg, TAG_A_FULL, o);
-                        // (ordered after the acquire on the mbarrier; no release needed: nothing of ours precedes it)
+                        // The slot's READ (async proxy) completed before this thread's acquire on the mbarrier returned, and
+                        // this store follows that wait in program order.  REVE_CONSUMED_RELEASE makes it a gpu-scope release,
+                        // which puts "read done" -> "slot may be overwritten" into the PTX causality order by the letter
+                        // (DESIGN.md section 4.1c); the relaxed form relies on a completed read being immune to later writes.
+#if REVE_CONSUMED_RELEASE
+                        st_release_gpu(p.flags + (link_in * 2 + 1) * kChainFlagStride + ps_b, static_cast<unsigned>(pk_b));
+#else
                         st_relaxed_gpu(p.flags + (link_in * 2 + 1) * kChainFlagStride + ps_b, static_cast<unsigned>(pk_b));
+#endif
                     }
                     const long long c1 = tr ? clock64() : 0;
                     const int s = seq.s, k = seq.k;

@@ -227,7 +227,9 @@ def test_segment_scheduler_on_the_gpu_two_lanes(exe, tmp_path):
             assert cv2.imwrite(str(d / f"frame{k + 1:08d}.png"), f[:, :, ::-1])
     keep = tmp_path / "kept"
     keep.mkdir()
-    r = subprocess.run([exe, "--segments", str(tmp_path), "-g", "0,0", "-v", "--random-weights", "-m", str(tmp_path / "none"),
+    import torch
+    lanes = "0,1" if torch.cuda.device_count() >= 2 else "0,0"     # two GPUs when the box has them
+    r = subprocess.run([exe, "--segments", str(tmp_path), "-g", lanes, "-v", "--random-weights", "-m", str(tmp_path / "none"),
                         "--encode-cmd", f"mkdir -p {keep}/{{index}} && cp {{out_dir}}/*.png {keep}/{{index}}/ && echo ok > {{part}}"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
