@@ -216,6 +216,7 @@ class Lane:
         self.dev = dev
         self.w, self.h, self.scale, _ = WORKLOADS[args.workload]
         torch.cuda.set_device(dev)
+        self.numa_cpus = None
         self.model = reve_b200.Model.for_scale(self.scale, args.model_dir, allow_random=True, seed=1234)
         self.up = reve_b200.Upscaler(self.model, self.w, self.h, tile=args.tile, prepad=args.prepad, device=dev, ring_depth=8,
                                      shared_device=args.shared_device)
@@ -227,6 +228,11 @@ class Lane:
         self.d_out = torch.empty((self.nres, self.h * self.scale, self.w * self.scale, 3), dtype=torch.uint8, device=f"cuda:{dev}")
         self.stream = torch.cuda.ExternalStream(self.up.stream, device=f"cuda:{dev}")
         self.ring = self.up.ring_depth
+        self.h_in = self.h_out = None
+
+    def alloc_pinned(self):
+        """Called from the lane's own thread (after it has bound itself to the GPU's NUMA node, --numa): the pinned ring is
+        first touched, hence placed, there."""
         self.h_in = [self.up.pinned((self.h, self.w, 3)) for _ in range(self.ring)]
         self.h_out = [self.up.pinned((self.h * self.scale, self.w * self.scale, 3)) for _ in range(self.ring)]
         for i in range(self.ring):
@@ -298,7 +304,11 @@ def measure(lanes, args, barrier, reduce_max, rank0: bool):
         lane = lanes[li]
         torch = lane.torch
         torch.cuda.set_device(lane.dev)
-        out = {}
+        if args.numa:
+            from reve_b200 import numa
+            lane.numa_cpus = numa.bind_thread_to_gpu_node(lane.dev)
+        lane.alloc_pinned()
+        out = {"numa_cpus": lane.numa_cpus}
         for _ in range(Wm):
             lane.step_device()
         torch.cuda.synchronize(lane.dev)
@@ -451,6 +461,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * out_bytes, "api": "reve_submit/reve_wait, pinned host buffers",
                     "host_checksum": results[0]["checksum"]},
             "latency_ms_1frame": results[0].get("latency_ms"),
+            "host": {"cores": os.cpu_count(), "numa_binding": [r.get("numa_cpus") for r in results] if args.numa else "off"},
             "gpu_launches": launches,
             "launch": results[0]["launch_info"],
             "roofline": {"kernel": (f"conv3x3_chain_kernel ({layers_per_launch:.0f} chained 64->64 3x3 + PReLU layers per launch, tcgen05, "
@@ -530,6 +541,8 @@ def main():
                     help="N GPUs from ONE process: one thread + one context per GPU, no process group at all")
     ap.add_argument("--pg", default="nccl", choices=["nccl", "gloo"], help="process group for barrier / MAX under torchrun")
     ap.add_argument("--shared-device", action="store_true", help="REVE_CTX_SHARED_DEVICE: single-layer launches only")
+    ap.add_argument("--numa", action="store_true",
+                    help="bind every lane's thread (and so its pinned ring) to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -56,8 +56,11 @@ const char* reve_strerror(int status);
 /* Message of the last failure on `ctx` (ctx == NULL: last failure of a context-free call on this
  * thread).  Never NULL; valid until the next failing call on the same context / thread. */
 const char* reve_last_error(const reve_ctx* ctx);
-/* Number of CUDA devices that can run the kernels (compute capability 10.x). */
+/* Number of CUDA devices that can run the kernels (compute capability 10.0). */
 int reve_device_count(int* n);
+/* PCI address of a device as sysfs spells it ("0000:1b:00.0"), so that a host can place the worker thread and the pinned
+ * buffers of a GPU on the NUMA node it hangs off (/sys/bus/pci/devices/<id>/numa_node); cap >= 16. */
+int reve_device_pci_bus_id(int device, char* buf, size_t cap);
 
 /* ---- model (replaces `-n realesr-animevideov3-x{s}` + the models\ directory) ---------------- */
 /* Parse an ncnn .param/.bin pair and validate that it is SRVGGNetCompact(3->64, 16 body convs,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "reve_strerror": (C.c_char_p, [C.c_int]),
     "reve_last_error": (C.c_char_p, [C.c_void_p]),
     "reve_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "reve_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t]),
     "reve_model_load_ncnn": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "reve_model_random": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "reve_model_from_arrays": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

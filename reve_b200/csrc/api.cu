@@ -766,6 +766,19 @@ int reve_device_count(int* n) {
     return REVE_OK;
 }
 
+int reve_device_pci_bus_id(int device, char* buf, size_t cap) {
+    if (!buf || cap < 16) return set_err(nullptr, REVE_E_INVAL, "buffer too small");
+    buf[0] = 0;
+    char tmp[32] = {};
+    const cudaError_t e = cudaDeviceGetPCIBusId(tmp, sizeof tmp, device);
+    if (e != cudaSuccess) return set_err(nullptr, e == cudaErrorInvalidDevice ? REVE_E_INVAL : REVE_E_CUDA, cuda_msg(nullptr, "cudaDeviceGetPCIBusId", e));
+    for (size_t i = 0; tmp[i] && i + 1 < cap; ++i) {
+        buf[i] = static_cast<char>(tmp[i] >= 'A' && tmp[i] <= 'F' ? tmp[i] - 'A' + 'a' : tmp[i]);   // sysfs uses lower case
+        buf[i + 1] = 0;
+    }
+    return REVE_OK;
+}
+
 int reve_model_load_ncnn(const char* param_path, const char* bin_path, reve_model** out) {
     if (!param_path || !bin_path || !out) return set_err(nullptr, REVE_E_INVAL, "NULL argument");
     *out = nullptr;

@@ -16,6 +16,7 @@
 // pull segments from the queue in `<temp>/video.temp` and run export(k+1) || upscale(k) || encode(k-1) each, see
 // run_segments() below.
 #include <dirent.h>
+#include <sched.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -274,6 +275,41 @@ void worker(const Options& o, const reve_model* model, int device, const std::ve
     lane.run(o.in, o.out, names, first, step, failed);
 }
 
+// Host placement (what the multi-GPU path shares is host cores, host DRAM and PCIe root complexes): the
+// calling thread -- and the pinned buffers it allocates next, and the pool threads it starts -- are restricted to the
+// CPUs of the NUMA node the GPU hangs off.  A no-op wherever sysfs does not say (single-node hosts report -1).
+int bind_thread_to_gpu_node(int device) {
+    char bdf[32];
+    if (reve_device_pci_bus_id(device, bdf, sizeof bdf) != REVE_OK) return 0;
+    auto slurp = [](const std::string& path) {
+        std::string out;
+        if (FILE* f = std::fopen(path.c_str(), "r")) {
+            char buf[4096];
+            const size_t n = std::fread(buf, 1, sizeof buf - 1, f);
+            std::fclose(f);
+            out.assign(buf, n);
+        }
+        return out;
+    };
+    const std::string node = slurp(std::string("/sys/bus/pci/devices/") + bdf + "/numa_node");
+    if (node.empty() || std::atoi(node.c_str()) < 0) return 0;
+    const std::string list = slurp("/sys/devices/system/node/node" + std::to_string(std::atoi(node.c_str())) + "/cpulist");
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (const char* p = list.c_str(); *p && *p != '\n';) {
+        char* e = nullptr;
+        const long a = std::strtol(p, &e, 10);
+        long b = a;
+        if (e == p) break;
+        if (*e == '-') b = std::strtol(e + 1, &e, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(static_cast<int>(c), &set); ++n; }
+        p = (*e == ',') ? e + 1 : e;
+    }
+    if (n == 0 || sched_setaffinity(0, sizeof set, &set) != 0) return 0;
+    return n;
+}
+
 std::vector<std::string> list_pngs(const std::string& dir, bool& ok) {
     std::vector<std::string> names;
     ok = false;
@@ -389,7 +425,10 @@ int run_segments(const Options& o, const reve_model* model) {
 
     std::vector<int> gpus = o.gpus.empty() ? std::vector<int>{0} : o.gpus;
     const int host_threads = std::max(2, static_cast<int>(std::thread::hardware_concurrency()) / static_cast<int>(gpus.size()) - 1);
+    std::atomic<long> frames_done{0};
+    const auto t_start = std::chrono::steady_clock::now();
     auto gpu_worker = [&](int gpu) {
+        if (!o.schedule_only) bind_thread_to_gpu_node(gpu);
         Lane lane(o, model, gpu, host_threads);
         auto do_export = [&](reve_host::Segment sg) {
             const std::string in_dir = temp + "/tmp_frames/" + std::to_string(sg.index);
@@ -428,6 +467,7 @@ int run_segments(const Options& o, const reve_model* model) {
                     std::string e;
                     if (!reve_host::png_read(in_dir + "/" + names[0], first, e) || !lane.prepare(first.w, first.h, e)) { set_error(e); failed = true; ok = false; }
                     if (ok) ok = lane.run(in_dir, out_dir, names, 0, 1, failed);
+                    if (ok) frames_done += static_cast<long>(names.size());
                 }
             }
             if (ok && !o.export_cmd.empty()) remove_dir(in_dir);       // main.rs:276-278
@@ -451,6 +491,9 @@ int run_segments(const Options& o, const reve_model* model) {
         std::fprintf(stderr, "error: %s\n", g_err.c_str());
         return 1;
     }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    std::fprintf(stderr, "[summary] %ld frames of %ld segments on %zu lanes in %.2f s (%.1f frames/s, start-up included)\n",
+                 frames_done.load(), video.segment_count, gpus.size(), secs, secs > 0 ? frames_done.load() / secs : 0.0);
     return 0;
 }
 

@@ -24,6 +24,9 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# every cv2.VideoCapture brings its own ffmpeg decoder threads (one per core by default): G captures on one host
+# oversubscribe it.  A handful per capture is what a real `ffmpeg -threads n` decode stage would be given.
+os.environ.setdefault("OPENCV_FFMPEG_CAPTURE_OPTIONS", "threads;" + os.environ.get("REVE_DECODE_THREADS", "2"))
 
 W, H, S = 1920, 1080, 2
 
@@ -92,6 +95,9 @@ def lane(dev: int, path: str, n: int, sink_kind: str, tmp: str, start: threading
     """stages: 'gpu' (pinned buffers cycled, no host stages), 'all' (decode -> gpu -> sink)."""
     import cv2
     import reve_b200
+    if NUMA:
+        from reve_b200 import numa
+        numa.bind_thread_to_gpu_node(dev)                  # inherited by the decoder / consumer threads started below
     model = reve_b200.Model.for_scale(S, "models", allow_random=True, seed=1234)
     ring = 8
     with reve_b200.Upscaler(model, W, H, tile=200, prepad=10, device=dev, ring_depth=ring) as up:
@@ -188,19 +194,26 @@ def run(gpus: int, path: str, n: int, sink_kind: str, tmp: str, stages: str) -> 
             "sink_busy_frac": float(np.mean([v["sink_busy_s"] / v["s"] for v in out.values()]))}
 
 
+NUMA = False
+
+
 def main():
+    global NUMA
     ap = argparse.ArgumentParser()
+    ap.add_argument("--numa", action="store_true", help="bind each GPU's three threads to the GPU's NUMA node")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--frames", type=int, default=240, help="frames per GPU")
     ap.add_argument("--sink", default="checksum", choices=["checksum", "mjpg"])
     a = ap.parse_args()
+    NUMA = a.numa
     tmp = tempfile.mkdtemp()
     clip = os.path.join(tmp, "clip.mp4")
     make_clip(clip, 48)
     cores = os.cpu_count()
     base = {"workload": "stand-in for BASELINE.json configs[4]: 1080p x2, decode + consumer overlapped with the upscale; "
                         "mp4v decode (OpenCV) and a " + a.sink + " sink -- NOT ffmpeg/x265 (absent from the image)",
-            "gpus": a.gpus, "frames_per_gpu": a.frames, "host_cores": cores}
+            "gpus": a.gpus, "frames_per_gpu": a.frames, "host_cores": cores, "numa": a.numa,
+            "decode_threads_per_capture": os.environ["OPENCV_FFMPEG_CAPTURE_OPTIONS"]}
     print(json.dumps(dict(base, stage="decode only, 1 thread", fps=round(decode_only(clip, 120), 1))), flush=True)
     print(json.dumps(dict(base, stage=f"{a.sink} sink only, 1 thread", fps=round(sink_only(a.sink, 60, tmp), 1))), flush=True)
     r = run(a.gpus, clip, a.frames, a.sink, tmp, "gpu")
