@@ -51,6 +51,9 @@ constexpr int kOffOut = kOffA + kStagesA * kTileA;
 constexpr int kOffTab = kOffOut + kEpiGroups * kStageOut;
 constexpr int kSmem = 1024 + kOffTab + kMaxTableInts * 4;
 
+#ifndef REVE_CONV0_WAIT_SLEEP
+#define REVE_CONV0_WAIT_SLEEP 0   // ns a waiting producer / epilogue warp sleeps between polls (0 = spin; see profiles/r02_notes.md)
+#endif
 enum : uint32_t { TAG0_W = 11, TAG0_EMPTY = 12, TAG0_FULL = 13, TAG0_ACC_EMPTY = 14, TAG0_ACC_FULL = 15 };
 
 // K-major, no swizzle: 8-row x 16-byte core matrices; LBO = distance between core matrices that
@@ -179,7 +182,7 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
                 w[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&b);
             }
             w[14] = w[15] = 0u;
-            mbar_wait(base + kBarEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG0_EMPTY, j);
+            mbar_wait_relaxed<REVE_CONV0_WAIT_SLEEP>(base + kBarEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG0_EMPTY, j);
             // element (row m, 16-byte k-chunk c) at (m/8)*512 + c*128 + (m%8)*16
             const uint32_t dst = base + kOffA + stage * kTileA + (m >> 3) * 512 + (m & 7) * 16;
 #pragma unroll
@@ -235,7 +238,7 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
                 const int cy = static_cast<int>(px / static_cast<unsigned>(CW)), cx = static_cast<int>(px - static_cast<unsigned>(cy) * CW);
                 keep = (tx[cx] >= 0) && (ty[cy] >= 0);
             }
-            mbar_wait(base + kBarAccFull + 8 * buf, ubuf & 1, dbg, TAG0_ACC_FULL, j);
+            mbar_wait_relaxed<REVE_CONV0_WAIT_SLEEP>(base + kBarAccFull + 8 * buf, ubuf & 1, dbg, TAG0_ACC_FULL, j);
             tc_fence_after();
             if (gleader) bulk_wait_read<0>();   // this group's previous tile has left the staging buffer
             named_bar_sync(1 + grp, 128);

@@ -42,6 +42,10 @@
 
 #include "model.h"
 
+#ifndef REVE_TAIL_WAIT_SLEEP
+#define REVE_TAIL_WAIT_SLEEP 0   // tail kernel: ns its TMA producer sleeps between polls of a full ring (0 = spin)
+#endif
+
 namespace reve {
 
 namespace {
@@ -360,7 +364,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if (seq.s == 0) cur0.next(strip, y, newseg); else cur1.next(strip, y, newseg);
                 const int x0 = (rev ? p.n_strips - 1 - strip : strip) * kStripPx;
                 const uint32_t stage = i % kStages, use = i / kStages;
-                mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                if constexpr (TAIL) mbar_wait_relaxed<REVE_TAIL_WAIT_SLEEP>(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
+                else mbar_wait(base + kBarAEmpty + 8 * stage, (use & 1) ^ 1, dbg, TAG_A_EMPTY, i);
                 if constexpr (PAIR) {
                     if (leader) mbar_arrive_expect_tx(base + kBarAFull + 8 * stage, 2 * kRowBytes);
                     tma_load_3d_hint_pair(base + kOffRing + stage * kRowBytes, &in_map, full_base + 8 * stage, 0,

@@ -78,6 +78,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugBl
         if (clock64() - t0 > (1ll << 32)) watchdog_fail(dbg, tag, aux, parity);
     }
 }
+// Same, for warps whose wait is long and off the critical path in a kernel that is bound by instruction issue: every
+// failed try_wait is followed by a nanosleep, so the waiting warp stops competing for issue slots with the working ones.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, DebugBlock* dbg,
+                                                  uint32_t tag, uint32_t aux = 0) {
+    if constexpr (SLEEP_NS <= 0) {
+        mbar_wait(bar, parity, dbg, tag, aux);
+    } else {
+        if (mbar_try_wait(bar, parity)) return;
+        const long long t0 = clock64();
+        while (!mbar_try_wait(bar, parity)) {
+            asm volatile("nanosleep.u32 %0;" ::"n"(SLEEP_NS));
+            if (clock64() - t0 > (1ll << 32)) watchdog_fail(dbg, tag, aux, parity);
+        }
+    }
+}
 
 // ---------------------------------------------------------------- async proxy / TMA
 __device__ __forceinline__ void fence_proxy_async_smem() {

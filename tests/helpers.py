@@ -70,7 +70,10 @@ def feature_report(dev: np.ndarray, ref: np.ndarray, rows: np.ndarray | None = N
     if rows is not None:
         dev, ref = dev[rows], ref[rows]
     err = np.abs(dev - ref)
-    tol = 2e-2 + 2e-2 * np.abs(ref)
+    # fp16 storage of 17 layers of activations against the fp32 oracle: the largest error / (1 + |ref|) measured over
+    # five geometries x two frame kinds x six layers is 3.84e-3 (tools/feature_errors.py, profiles/r02_feature_errors.txt);
+    # the tolerance is twice that
+    tol = 8e-3 + 8e-3 * np.abs(ref)
     bad = err > tol
     rep = {"max_err": float(err.max()), "mean_err": float(err.mean()), "bad_frac": float(bad.mean()),
            "ref_absmax": float(np.abs(ref).max())}

@@ -2,7 +2,8 @@
 
 Acceptance bar (BASELINE.json north_star): >= 99.9 % of u8 pixels within +-1 LSB and PSNR >= 50 dB
 against the fp32 oracle evaluated with identical tile / pre-pad semantics.  Activations are stored
-as fp16 on the device, so intermediate features are compared with a tolerance of 2e-2 + 2e-2*|ref|.
+as fp16 on the device, so intermediate features are compared with a tolerance of 8e-3 + 8e-3*|ref| (twice the largest
+error measured, tests/helpers.py).
 """
 import ctypes as C
 import glob
@@ -527,7 +528,7 @@ def test_fp16_range_stress_large_activations():
         d, r = dev[rows], ref[rows]
         assert np.isfinite(d).all()
         peak = max(peak, float(np.abs(r).max()))
-        bad = np.abs(d - r) > gain * 2e-2 + 2e-2 * np.abs(r)
+        bad = np.abs(d - r) > gain * 8e-3 + 8e-3 * np.abs(r)       # the tolerance of tests/helpers.py, scaled with the activations
         assert bad.mean() == 0.0, (layer, float(np.abs(d - r).max()), float(np.abs(r).max()))
     assert 1e3 < peak < 6e4, peak                    # the stress actually reached the upper fp16 decades, without overflow
     check(out, srvgg.upscale(frame, wts, tile=0, prepad=10))                       # fp32 oracle
