@@ -260,7 +260,9 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
             const int chains = c.total_rows < ctx->n_chains ? c.total_rows : ctx->n_chains;
             CK(ctx, cudaMemsetAsync(ctx->d_chain_flags, 0, ctx->chain_flag_bytes, ctx->s_comp));
             // self-balancing split (ChainParams::speed_in): full grids with enough rows per chain to measure
-            const bool balance = ctx->d_chain_speed && chains == ctx->n_chains && c.total_rows >= 256 * chains;
+            // (a forced launch structure -- tests, sanitizer runs -- takes the balanced path at any size: a short launch reads
+            // the table and hands the old figures on)
+            const bool balance = ctx->d_chain_speed && chains == ctx->n_chains && (c.total_rows >= 256 * chains || ctx->chain_forced);
             if (balance) {
                 float* const pair = ctx->d_chain_speed + 128 * (k / L);
                 c.speed_in = pair + 64 * (ctx->chain_launches[k / L] & 1u);

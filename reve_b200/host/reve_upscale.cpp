@@ -567,7 +567,8 @@ int run_raw(const Options& o, const reve_model* model) {
 #endif
     const int w = o.raw_w, h = o.raw_h, ring = 8, depth = 12;   // 8 frames inside the library, 4 more being read / written
     reve_ctx* ctx = nullptr;
-    if (reve_ctx_create(o.gpus.empty() ? 0 : o.gpus[0], model, w, h, o.tile, o.prepad, ring, &ctx) != REVE_OK) {
+    // frames smaller than the pre-pad: upstream's reflect-101 reads out of bounds there; pad as far as it is defined
+    if (reve_ctx_create(o.gpus.empty() ? 0 : o.gpus[0], model, w, h, o.tile, std::min(o.prepad, std::min(w, h) - 1), ring, &ctx) != REVE_OK) {
         std::fprintf(stderr, "error: %s\n", reve_last_error(nullptr));
         return 1;
     }
