@@ -61,6 +61,15 @@ def config_block(args, world: int, parallelism: str) -> dict:
             "parallelism": parallelism}
 
 
+def parallelism_string(args, n_gpus: int) -> str:
+    """Identical on both arms for the same command line (the reference arm describes the configuration of OUR arm)."""
+    if n_gpus <= 1:
+        return "segments x1, no collective"
+    mode = ("one process, one thread + reve_ctx per GPU (the product's shape)" if args.single_process else
+            f"one rank per GPU under torchrun ({args.pg} process group for barrier / MAX only)")
+    return f"segments x{n_gpus}, no collective; {mode}"
+
+
 def measured_traffic(chained=False):
     """dram__bytes_read.sum + dram__bytes_write.sum of one body launch from the committed ncu capture."""
     for name in (("r02_chain_traffic.json", "r01_chain_traffic.json") if chained else ("r01_body_traffic.json",)):
@@ -189,7 +198,7 @@ def run_reference(args):
         "impl": "reference", "metric": metric_name(args.workload), "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v if v else None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_block(args, 1, "segments x1, no collective"),
+        "config": config_block(args, args.gpus, parallelism_string(args, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "per step: " + desc},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -446,13 +455,11 @@ def run_ours(args):
         conv0_bytes = in_bytes + canvas_px * 128
         tail_bytes = canvas_px * 128 + in_bytes + out_bytes
         conv0_ms, tail_ms = pr["ms_conv0"] / frames_timed, pr["ms_tail"] / frames_timed
-        mode = ("one process, one thread + reve_ctx per GPU (the product's shape)" if single else
-                f"one rank per GPU under torchrun ({args.pg} process group for barrier / MAX only)") if n_gpus > 1 else "1 GPU"
         line = {
             "metric": metric_name(args.workload), "value": fps, "unit": "frames/s", "n_gpus": n_gpus, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
-            "config": config_block(args, n_gpus, f"segments x{n_gpus}, no collective; {mode}"),
+            "config": config_block(args, n_gpus, parallelism_string(args, n_gpus)),
             "regions": {"count": len(regions), "frames_each": K * B, "ms": regions, "e2e_ms": e2e, "reported": "median"},
             "output_mpixel_per_s": fps * px * scale * scale / 1e6,
             "frame_tflops_algorithmic": frame_tflops,

@@ -33,6 +33,11 @@ def test_both_arms_describe_the_same_config():
     assert t and t["dram_bytes_per_launch"] == t["dram_bytes_read"] + t["dram_bytes_write"]
     assert t["dram_bytes_per_frame"] > 100 * t["algorithmic_minimum_bytes_per_frame"] / 1.1   # ~110x, stated, not hidden
     json.dumps(a)
+    # the same command line gives the same block on both arms, value for value
+    args = argparse.Namespace(workload="1080p_x2", tile=200, prepad=10, batch=12, single_process=False, pg="nccl", gpus=1)
+    ours = bench.config_block(args, 1, bench.parallelism_string(args, 1))
+    ref = bench.config_block(args, args.gpus, bench.parallelism_string(args, args.gpus))
+    assert ours == ref and ours["parallelism"] == "segments x1, no collective"
 
 
 def test_numa_helper_reads_sysfs(tmp_path, monkeypatch):
