@@ -1102,7 +1102,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             uint32_t w_row = w_lo + (2 - (k + 1) % 3) * kRot;
             asm volatile("" : "+r"(w_row));
             const uint32_t d = tmem_base + s * kBank;
-            if (p.trace && chain == static_cast<unsigned>(p.trace_chain) && i >= 200 && i < 700 && lane == 0) p.trace[j * 512 + i - 200] = clock64();
+            if (p.trace && chain == static_cast<unsigned>(p.trace_chain) && i >= 200 && i < 692 && lane == 0) p.trace[j * 512 + i - 200] = clock64();
             if (elected) {
 #pragma unroll
                 for (int dxk = 0; dxk < 4; ++dxk)
@@ -1126,8 +1126,17 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                 umma_commit(base + kBarAccFull + 8 * (s * 3 + (k - 1) % 3));
             }
             if (!ok) {
+                // (trace: what the next step had to wait for -- its input row, or the accumulator slot the epilogue returns)
+                const bool tw = p.trace && chain == static_cast<unsigned>(p.trace_chain) && lane == 0;
+                const long long w0 = tw ? clock64() : 0;
                 mbar_wait(g.bar_f, g.par_f, dbg, TAG_A_FULL, i + 1);
+                const long long w1 = tw ? clock64() : 0;
                 if (g.need_e) mbar_wait(g.bar_e, g.par_e, dbg, TAG_ACC_EMPTY, seq.k);
+                if (tw) {
+                    p.trace[j * 512 + 492] += w1 - w0;            // cycles waiting for A
+                    p.trace[j * 512 + 493] += clock64() - w1;     // cycles waiting for an empty accumulator slot
+                    p.trace[j * 512 + 494] += 1;                  // steps that had to wait at all
+                }
             }
             tc_fence_after();
             ++i;

@@ -22,9 +22,10 @@ for _ in range(3):
 tr = np.zeros(4096, np.int64)
 assert _lib.load().reve_debug_trace(up._h, tr.ctypes.data, 4096) == 0
 for j in range(L):
-    t = tr[512 * j:512 * j + 500]
+    t = tr[512 * j:512 * j + 492]
     t = t[t > 0]
     d = np.diff(t)
+    d = d[(d > 0) & (d < 100000)]     # (entries of an earlier launch with more steps may linger at the end)
     c = tr[512 * j + 500:512 * j + 508]
     line = f"layer {j}: steps {len(t)}"
     if len(d):
@@ -33,6 +34,11 @@ for j in range(L):
         line += f" | courier/row: wait_full {c[0] / c[3]:.0f} store {c[1] / c[3]:.0f} publish {c[2] / c[3]:.0f}"
     if c[7]:
         line += f" | loader/step: retire {c[4] / c[7]:.0f} poll {c[5] / c[7]:.0f} a_empty {c[6] / c[7]:.0f}"
+    m = tr[512 * j + 492:512 * j + 496]
+    if c[7]:
+        runs = 3     # the counters accumulate over the three traced launches above
+        line += (f" | MMA issuer/step: wait for A {m[0] / c[7] / runs:.0f} wait for slot {m[1] / c[7] / runs:.0f} "
+                 f"({100 * m[2] / c[7] / runs:.0f} % of steps waited)")
     print(line)
 
 # per-CTA wall clock (globaltimer, ns): kernel-relative start of the MMA warp, first step, end of the last step
