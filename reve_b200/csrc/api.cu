@@ -96,7 +96,7 @@ struct reve_ctx {
     // sweep direction and needed rows, i.e. in which part of the canvas a chain works on), swapped every time it runs
     float* d_chain_speed = nullptr;   // [kNumBody / 2][2][64] floats
     unsigned chain_launches[kNumBody / 2] = {};
-    CUtensorMap map_chain_scratch, map_chain_out[2];
+    CUtensorMap map_chain_scratch, map_chain_scratch_q, map_chain_out[2], map_chain_out_q[2], map_chain_out_e[2];
     ChainParams chain[kNumBody / 2];
     DebugBlock* dbg_host = nullptr;
     DebugBlock* dbg_dev = nullptr;
@@ -269,7 +269,8 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
                 c.speed_out = pair + 64 * ((ctx->chain_launches[k / L] + 1u) & 1u);
             }
             {
-                const cudaError_t le = launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, c);
+                const cudaError_t le = launch_conv_chain(ctx->s_comp, chains * L, ctx->map_in[cur], ctx->map_chain_out[cur ^ 1], ctx->map_chain_scratch, ctx->map_chain_scratch_q,
+                                                         ctx->map_chain_out_q[cur ^ 1], ctx->map_chain_out_e[cur ^ 1], c);
                 if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
                     // the device (as partitioned right now) cannot hold the grid: nothing was launched; these layers
                     // and every later batch run as single-layer launches, which never wait for another CTA
@@ -672,9 +673,17 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
                                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return set_err(ctx, REVE_E_CUDA, "cuTensorMapEncodeTiled (chain scratch map) failed");
+            const cuuint32_t box_q[2] = {64, 32};   // a quarter of a row: what one epilogue warp writes and its TMA store ships
+            const CUresult rq = enc(&ctx->map_chain_scratch_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ctx->d_chain_scratch, gdim,
+                                    gstride, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rq != CUDA_SUCCESS) return set_err(ctx, REVE_E_CUDA, "cuTensorMapEncodeTiled (chain scratch quarter map) failed");
         }
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i) {
             if ((rc = encode_map(ctx, enc, &ctx->map_chain_out[i], ctx->act[i], cw, ch, P))) return rc;
+            if ((rc = encode_map(ctx, enc, &ctx->map_chain_out_q[i], ctx->act[i], cw, ch, 32))) return rc;
+            if ((rc = encode_map(ctx, enc, &ctx->map_chain_out_e[i], ctx->act[i], cw, ch, 32 - L))) return rc;
+        }
         for (int c = 0; c < kNumBody / L; ++c) {
             ChainParams& p = ctx->chain[c];
             p = ChainParams{};

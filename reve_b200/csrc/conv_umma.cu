@@ -82,10 +82,10 @@ constexpr int kBarAFull = 16;
 constexpr int kBarAEmpty = kBarAFull + 8 * kMaxStages;
 constexpr int kBarAccFull = kBarAEmpty + 8 * kMaxStages;   // [stream][slot]
 constexpr int kBarAccEmpty = kBarAccFull + 8 * 6;           // [stream][slot]
-constexpr int kBarStgFull = kBarAccEmpty + 8 * 6;          // chain kernel: [group] staging buffer written
-constexpr int kBarStgFree = kBarStgFull + 8 * 2;           // chain kernel: [group] staging buffer read by the TMA store
+constexpr int kBarStgFull = kBarAccEmpty + 8 * 6;          // chain kernel: [group][quarter] staging buffer written
+constexpr int kBarStgFree = kBarStgFull + 8 * 8;           // chain kernel: [group][quarter] staging buffer read by the TMA store
 constexpr int kTmemPtr = 512;
-static_assert(kBarStgFree + 8 * 2 <= kTmemPtr, "control block overflow");
+static_assert(kBarStgFree + 8 * 8 <= kTmemPtr, "control block overflow");
 constexpr int kOffBias = 1024;   // 64 floats
 constexpr int kOffSlope = 1280;  // 64 floats
 static_assert(kBarAccEmpty + 8 * 6 <= kTmemPtr, "control block overflow");
@@ -824,6 +824,21 @@ struct ChainCursor {
 #ifndef REVE_CONSUMED_RELEASE
 #define REVE_CONSUMED_RELEASE 0
 #endif
+// Hand-over staging in quarters: every epilogue warp owns the 32 pixel rows (4 KB) it writes, with its own full / free
+// barriers and its own TMA store.  With ONE buffer per group a row can be written only after the previous row's 16 KB
+// have been read out by the TMA store -- at ~15 B/clk, because the tensor core's operand reads have the shared memory --
+// so write (~700 clk) and read-out (~1100) are strictly serial and leave 25 % slack in a stream's row period; one
+// step in ten then waits ~700 clk for an accumulator slot (profiles/r02_notes.md section 12).  In quarters a warp waits
+// for the read-out of its own 4 KB only, and the read-out of a row starts while the other warps still compute.
+#ifndef REVE_STAGE_QUARTERS
+#define REVE_STAGE_QUARTERS 1
+#endif
+// The chain's last layer stores its canvas rows the same way: every epilogue warp ships the valid pixels it wrote (32, or
+// 32 - C at the two ends of the box) with its own TMA store and waits for ITS previous read-out only; no barrier across
+// the group is left in that path.
+#ifndef REVE_LAST_QUARTERS
+#define REVE_LAST_QUARTERS 1
+#endif
 #ifndef REVE_PUBLISH_EVERY
 #define REVE_PUBLISH_EVERY 2
 #endif
@@ -833,7 +848,9 @@ constexpr int kChainThreads = kConvThreads + 64;   // + one courier warp per epi
 
 __global__ void __launch_bounds__(kChainThreads, 1)
 conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                     const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ ChainParams p) {
+                     const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ CUtensorMap scratch_map_q,
+                     const __grid_constant__ CUtensorMap out_map_q, const __grid_constant__ CUtensorMap out_map_e,
+                     const __grid_constant__ ChainParams p) {
     constexpr int NG = 64;
     constexpr int kStages = ring_stages(NG, false, false);
     constexpr int kRowsDx = rows_per_dx(NG, false);
@@ -873,8 +890,15 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             mbar_init(base + kBarAccEmpty + 8 * s, 4);
         }
         for (int s = 0; s < 2; ++s) {
+#if REVE_STAGE_QUARTERS
+            for (int q = 0; q < 4; ++q) {               // [group s][quarter q]: one arrive by the warp / by the courier
+                mbar_init(base + kBarStgFull + 8 * (4 * s + q), 1);
+                mbar_init(base + kBarStgFree + 8 * (4 * s + q), 1);
+            }
+#else
             mbar_init(base + kBarStgFull + 8 * s, 4);   // one arrive per warp of the group
             mbar_init(base + kBarStgFree + 8 * s, 1);
+#endif
         }
         fence_mbar_init();
     }
@@ -884,8 +908,8 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     }
     if (warp == 0 && lane == 0) {
         if (first) prefetch_tmap(&in_map);
-        if (last) prefetch_tmap(&out_map);
-        if (C > 1) prefetch_tmap(&scratch_map);
+        if (last) { prefetch_tmap(&out_map); prefetch_tmap(&out_map_q); prefetch_tmap(&out_map_e); }
+        if (C > 1) { prefetch_tmap(&scratch_map); prefetch_tmap(&scratch_map_q); }
     }
     tc_fence_before();
     __syncthreads();
@@ -966,7 +990,12 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             };
             for (int r = 0; r < n_rows_out; ++r) {
                 const long long c0 = tr ? clock64() : 0;
+#if REVE_STAGE_QUARTERS
+                const uint32_t full0 = base + kBarStgFull + 8 * (4 * grp), free0 = base + kBarStgFree + 8 * (4 * grp);
+                mbar_wait(full0, r & 1, dbg, TAG_STG_FULL, r);
+#else
                 mbar_wait(base + kBarStgFull + 8 * grp, r & 1, dbg, TAG_STG_FULL, r);
+#endif
                 const long long c1 = tr ? clock64() : 0;
                 // slot (r mod kChainSlots) last held row r - kChainSlots of this stream (rows are published 1-based)
                 if (cons_seen < r + 1 - kChainSlots) {
@@ -974,6 +1003,29 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                     flag_wait_ge(cons_flag, r + 1 - kChainSlots, cons_seen, dbg, TAG_CHAIN_CONS);
                     fence_proxy_async_global();
                 }
+#if REVE_STAGE_QUARTERS
+                // one store per quarter as soon as its warp has written it; a quarter is handed back when ITS read-out is done
+                const int row0 = (slot_base + r % kChainSlots) * kBoxPx;
+                tma_store_2d(&scratch_map_q, stg, 0, row0);
+                bulk_commit();
+#pragma unroll
+                for (int q = 1; q < 4; ++q) {
+                    mbar_wait(full0 + 8 * q, r & 1, dbg, TAG_STG_FULL, r);
+                    tma_store_2d(&scratch_map_q, stg + q * 4096, 0, row0 + 32 * q);
+                    bulk_commit();
+                }
+                bulk_wait_read<3>();
+                mbar_arrive(free0);
+                bulk_wait_read<2>();
+                mbar_arrive(free0 + 8);
+                bulk_wait_read<1>();
+                mbar_arrive(free0 + 16);
+                bulk_wait_read<0>();
+                mbar_arrive(free0 + 24);
+                const long long c2 = tr ? clock64() : 0;
+                if (r + 1 - published >= kChainPublishEvery && !(r + 1 < n_rows_out && mbar_test_wait(full0, (r + 1) & 1)))
+                    publish(r + 1);
+#else
                 tma_store_2d(&scratch_map, stg, 0, (slot_base + r % kChainSlots) * kBoxPx);
                 bulk_commit();
                 bulk_wait_read<0>();
@@ -982,6 +1034,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                 if (r + 1 - published >= kChainPublishEvery &&
                     !(r + 1 < n_rows_out && mbar_test_wait(base + kBarStgFull + 8 * grp, (r + 1) & 1)))
                     publish(r + 1);
+#endif
                 if (tr) {
                     const long long c3 = clock64();
                     t_full += c1 - c0; t_store += c2 - c1; t_pub += c3 - c2;
@@ -1215,16 +1268,29 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
 
             const uint32_t stg = base + kOffStage + grp * kRowBytes;
             if (last) {
+#if REVE_LAST_QUARTERS
+                if (lane == 0) bulk_wait_read<0>();        // this warp's previous store has read its quarter out
+                __syncwarp();
+#else
                 if (gleader) bulk_wait_read<0>();          // the previous row has left the staging buffer
                 named_bar_sync(1 + grp, 128);
+#endif
             } else if (sent > 0) {
+#if REVE_STAGE_QUARTERS
+                mbar_wait(base + kBarStgFree + 8 * (4 * grp + q), (sent - 1) & 1, dbg, TAG_STG_FREE, sent);   // this warp's quarter of row sent-1 has been read out
+#else
                 mbar_wait(base + kBarStgFree + 8 * grp, (sent - 1) & 1, dbg, TAG_STG_FREE, sent);   // courier has read row sent-1
+#endif
             }
             // last layer: box rows mlo..mhi become staging rows 0..P-1 (the stored box); other layers hand on the
             // whole 128-row tile in place (rows outside the valid range as zeros)
             const bool writes = last ? (m >= mlo && m <= mhi) : true;
             if (writes) {
+#if REVE_LAST_QUARTERS
+                const int row = m;                         // every layer stages its pixels in place
+#else
                 const int row = last ? m - mlo : m;
+#endif
                 const uint32_t rbase = stg + row * 128;
                 if (keep) {
 #pragma unroll
@@ -1249,20 +1315,39 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             }
             fence_proxy_async_smem();
             if (last) {
+#if REVE_LAST_QUARTERS
+                __syncwarp();
+                if (lane == 0) {
+                    // pixels [32q, 32q+32) of the box, clipped to the layer's valid range [mlo, mhi]: the two end quarters
+                    // are 32 - C pixels wide (mlo = C, mhi = 127 - C)
+                    const int m0 = (q == 0) ? mlo : 32 * q;
+                    tma_store_3d((q == 0 || q == 3) ? &out_map_e : &out_map_q, stg + m0 * 128, 0, seg_xb + m0, pr);
+                    bulk_commit();
+                }
+#else
                 named_bar_sync(1 + grp, 128);
                 if (gleader) {
                     tma_store_3d(&out_map, stg, 0, seg_xb + C, pr);
                     bulk_commit();
                 }
+#endif
             } else {
                 __syncwarp();
+#if REVE_STAGE_QUARTERS
+                if (lane == 0) mbar_arrive(base + kBarStgFull + 8 * (4 * grp + q));
+#else
                 if (lane == 0) mbar_arrive(base + kBarStgFull + 8 * grp);
+#endif
             }
             ++sent;
         }
     }
 
+#if REVE_LAST_QUARTERS
+    if (last && warp >= 2 && warp < 10 && lane == 0) bulk_wait<0>();
+#else
     if (last && warp >= 2 && warp < 10 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -1338,7 +1423,8 @@ int chain_max_resident_ctas(int sm_count) {
 }
 
 cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
-                              const CUtensorMap& scratch_map, const ChainParams& p) {
+                              const CUtensorMap& scratch_map, const CUtensorMap& scratch_map_q, const CUtensorMap& out_map_q,
+                              const CUtensorMap& out_map_e, const ChainParams& p) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
     cfg.blockDim = dim3(kChainThreads, 1, 1);
@@ -1349,7 +1435,7 @@ cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_m
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv3x3_chain_kernel, in_map, out_map, scratch_map, p);
+    return cudaLaunchKernelEx(&cfg, conv3x3_chain_kernel, in_map, out_map, scratch_map, scratch_map_q, out_map_q, out_map_e, p);
 }
 
 cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map,

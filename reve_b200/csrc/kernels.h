@@ -89,8 +89,12 @@ inline size_t chain_scratch_rows(int n_chains, int len) { return static_cast<siz
 // grid = n_chains * len CTAs, all of which must be resident at the same time (one per SM): launched cooperatively, so
 // the driver guarantees it or refuses the launch (cudaErrorCooperativeLaunchTooLarge)
 int chain_max_resident_ctas(int sm_count);   // 0 when the device cannot launch cooperatively
+// scratch_map: the hand-over rings as [rows][64 ch] with a 128-pixel box (loads); scratch_map_q: the same memory with a
+// 32-pixel box (the senders store a row in quarters, one per epilogue warp)
+// out_map_q / out_map_e: the output canvas with boxes of 32 and 32 - len pixels (the last layer stores a row in quarters too)
 cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_map, const CUtensorMap& out_map,
-                              const CUtensorMap& scratch_map, const ChainParams& p);
+                              const CUtensorMap& scratch_map, const CUtensorMap& scratch_map_q, const CUtensorMap& out_map_q,
+                              const CUtensorMap& out_map_e, const ChainParams& p);
 
 // First convolution (3 -> 64) + PReLU on tensor cores (K = 27 padded to 32), fused with the u8 -> fp16
 // unpack, the reflect-101 pre-pad gather and the canvas layout (conv0.cu).
