@@ -71,7 +71,7 @@ struct reve_ctx {
     int n_strips = 0;
     std::vector<int> pending;  // ring slots whose H2D copy is issued but whose kernels are not yet enqueued
     void* d_wblob[kNumConv] = {};  // per layer: forward-sweep blob followed by the reverse-sweep blob
-    CUtensorMap map_in[2], map_out[2];
+    CUtensorMap map_in[2], map_out[2], map_out_q[2];   // input boxes of 128 px; output boxes of 31 px (map_out) and 32 px (map_out_q)
     CUtensorMap map_flat0;   // act[0] as a flat [pixels][64] tensor (conv0 output tiles of 128 pixels)
     void* d_w0 = nullptr;    // conv0 B operand
     Conv0Params c0;
@@ -293,7 +293,7 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
         // the sweep direction is baked into the layer's weight blob; the canvases alternate with every launch
         set_row_space(ctx, b, kNumBody - k, n, ch);   // body layer k is followed by 16 - k convolutions
         const int grid = b.total_rows < ctx->grid ? b.total_rows : ctx->grid;
-        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->pair && grid >= 2, ctx->map_in[cur], ctx->map_out[cur ^ 1], b));
+        CK(ctx, launch_conv_body(ctx->s_comp, grid, ctx->pair && grid >= 2, ctx->map_in[cur], ctx->map_out_q[cur ^ 1], ctx->map_out[cur ^ 1], b));
         ctx->prof.launches_body++;
         ctx->prof.body_frames += n;
         ctx->prof.body_layer_frames += n;
@@ -551,13 +551,14 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
     for (int i = 0; i < 2; ++i) {
         if ((rc = encode_map(ctx, enc, &ctx->map_in[i], ctx->act[i], cw, ch, kBoxPx))) return rc;
-        if ((rc = encode_map(ctx, enc, &ctx->map_out[i], ctx->act[i], cw, ch, kStripPx))) return rc;
+        if ((rc = encode_map(ctx, enc, &ctx->map_out[i], ctx->act[i], cw, ch, 31))) return rc;
+        if ((rc = encode_map(ctx, enc, &ctx->map_out_q[i], ctx->act[i], cw, ch, 32))) return rc;
     }
 
     {
         const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(cw) * ch};
         const cuuint64_t gstride[1] = {128};
-        const cuuint32_t box[2] = {64, 128};
+        const cuuint32_t box[2] = {64, 32};     // a quarter of a 128-pixel tile: one TMA store per epilogue warp
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&ctx->map_flat0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ctx->act[0], gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -74,6 +74,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 __global__ void __launch_bounds__(kThreads, 1)
 conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ Conv0Params p) {
+    // out_map: the output canvas as a flat [pixels][64 ch] tensor with a 32-pixel box: every epilogue warp stores the
+    // quarter of the tile it wrote with its own TMA store (as the chained body kernel does).
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -226,7 +228,6 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const bool gleader = (q == 0 && lane == 0);
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
             if ((j % kEpiGroups) != static_cast<uint32_t>(grp)) continue;
@@ -240,8 +241,8 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
             }
             mbar_wait_relaxed<REVE_CONV0_WAIT_SLEEP>(base + kBarAccFull + 8 * buf, ubuf & 1, dbg, TAG0_ACC_FULL, j);
             tc_fence_after();
-            if (gleader) bulk_wait_read<0>();   // this group's previous tile has left the staging buffer
-            named_bar_sync(1 + grp, 128);
+            if (lane == 0) bulk_wait_read<0>();   // this warp's previous store has read its quarter of the staging buffer out
+            __syncwarp();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t acc[32];
@@ -273,13 +274,13 @@ conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_cons
                 }
             }
             fence_proxy_async_smem();
-            named_bar_sync(1 + grp, 128);
-            if (gleader) {
-                tma_store_2d(&out_map, stg, 0, tile * 128);
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&out_map, stg + q * 4096, 0, tile * 128 + q * 32);
                 bulk_commit();
             }
         }
-        if (gleader) bulk_wait<0>();
+        if (lane == 0) bulk_wait<0>();
     }
 
     tc_fence_before();

@@ -235,8 +235,10 @@ constexpr int conv_threads(bool tail) { return tail ? kConvThreads + 32 : kConvT
 
 template <int NG, bool TAIL, bool PAIR>
 __global__ void __launch_bounds__(conv_threads(TAIL), 1)
-conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    const __grid_constant__ ConvParams p) {
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map_q,
+                    const __grid_constant__ CUtensorMap out_map_e, const __grid_constant__ ConvParams p) {
+    // body: out_map_q / out_map_e = the output canvas with boxes of 32 and 31 pixels (every epilogue warp stores the
+    // pixels it wrote with its own TMA store: the quarters of the row, the two end quarters one halo pixel short)
     constexpr int kStages = ring_stages(NG, TAIL, PAIR);
     constexpr int kRowsDx = rows_per_dx(NG, PAIR);
     constexpr int kWBytes = w_smem_bytes(NG, PAIR);
@@ -285,7 +287,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&in_map);
-        if (!TAIL) prefetch_tmap(&out_map);
+        if (!TAIL) { prefetch_tmap(&out_map_q); prefetch_tmap(&out_map_e); }
     }
     const uint32_t* rowtab = p.rowpack;
     if constexpr (TAIL) {
@@ -596,11 +598,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 
             if constexpr (!TAIL) {
                 const uint32_t stg = base + kOffStage + grp * kRowBytes;
-                const bool gleader = (q == 0 && lane == 0);
-                if (gleader) bulk_wait_read<0>();   // this group's previous row has left the staging buffer
-                named_bar_sync(1 + grp, 128);
+                if (lane == 0) bulk_wait_read<0>();   // this warp's previous store has read its quarter of the staging buffer out
+                __syncwarp();
                 if (m >= 1 && m <= kStripPx) {
-                    const int row = m - 1;
+                    const int row = m;                  // staged in place: pixel m of the box is row m
                     const uint32_t rbase = stg + row * 128;
                     if (ev.keep) {
 #pragma unroll
@@ -628,9 +629,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1 + grp, 128);
-                if (gleader) {
-                    tma_store_3d(&out_map, stg, 0, x0, pr);
+                __syncwarp();
+                if (lane == 0) {
+                    // pixels [32q, 32q+32) of the box without its two halo pixels 0 and 127; box pixel m is canvas column x0-1+m
+                    const int m0 = (q == 0) ? 1 : 32 * q;
+                    tma_store_3d((q == 0 || q == 3) ? &out_map_e : &out_map_q, stg + m0 * 128, 0, x0 - 1 + m0, pr);
                     bulk_commit();
                 }
                 if (tr) tr[3] = clock64();
@@ -757,7 +760,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         }
     }
 
-    if (!TAIL && warp >= 2 && (warp & 3) == 0 && lane == 0) bulk_wait<0>();
+    if (!TAIL && warp >= 2 && warp < 10 && lane == 0) bulk_wait<0>();
     tc_fence_before();
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
@@ -1438,8 +1441,8 @@ cudaError_t launch_conv_chain(cudaStream_t st, int grid, const CUtensorMap& in_m
     return cudaLaunchKernelEx(&cfg, conv3x3_chain_kernel, in_map, out_map, scratch_map, scratch_map_q, out_map_q, out_map_e, p);
 }
 
-cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map,
-                             const ConvParams& p) {
+cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map_q,
+                             const CUtensorMap& out_map_e, const ConvParams& p) {
     if (pair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(grid & ~1), 1, 1);
@@ -1453,17 +1456,17 @@ cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtenso
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<64, false, true>, in_map, out_map, p);
+        return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<64, false, true>, in_map, out_map_q, out_map_e, p);
     }
-    conv3x3_umma_kernel<64, false, false><<<grid, kConvThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map, p);
+    conv3x3_umma_kernel<64, false, false><<<grid, kConvThreads, smem_bytes_t<64, false, false>(), st>>>(in_map, out_map_q, out_map_e, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p) {
     switch (scale) {
-        case 2: conv3x3_umma_kernel<16, true, false><<<grid, conv_threads(true), smem_bytes_t<16, true, false>(), st>>>(in_map, in_map, p); break;
-        case 3: conv3x3_umma_kernel<32, true, false><<<grid, conv_threads(true), smem_bytes_t<32, true, false>(), st>>>(in_map, in_map, p); break;
-        case 4: conv3x3_umma_kernel<48, true, false><<<grid, conv_threads(true), smem_bytes_t<48, true, false>(), st>>>(in_map, in_map, p); break;
+        case 2: conv3x3_umma_kernel<16, true, false><<<grid, conv_threads(true), smem_bytes_t<16, true, false>(), st>>>(in_map, in_map, in_map, p); break;
+        case 3: conv3x3_umma_kernel<32, true, false><<<grid, conv_threads(true), smem_bytes_t<32, true, false>(), st>>>(in_map, in_map, in_map, p); break;
+        case 4: conv3x3_umma_kernel<48, true, false><<<grid, conv_threads(true), smem_bytes_t<48, true, false>(), st>>>(in_map, in_map, in_map, p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

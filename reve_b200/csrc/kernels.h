@@ -119,7 +119,9 @@ void pack_conv_weights(const float* w_oihw, int co, int ng, bool reverse, uint16
 
 cudaError_t conv_kernels_init();  // opt-in shared memory attributes; call once per device
 // `pair`: launch as clusters of two CTAs driving tcgen05.mma.cta_group::2 (grid rounded down to even)
-cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map, const ConvParams& p);
+// out_map_q / out_map_e: the output canvas with boxes of 32 and 31 pixels (one TMA store per epilogue warp)
+cudaError_t launch_conv_body(cudaStream_t st, int grid, bool pair, const CUtensorMap& in_map, const CUtensorMap& out_map_q,
+                             const CUtensorMap& out_map_e, const ConvParams& p);
 cudaError_t launch_conv_tail(cudaStream_t st, int grid, int scale, const CUtensorMap& in_map, const ConvParams& p);
 // 8-bit RGB -> yuv420p10le (yuv.cu).  Integer coefficients scaled by 2^16; matrix = 601 or 709.
 struct YuvCoeffs {
