@@ -33,8 +33,9 @@
 //     the centre of every padded tile, so the work of a layer is a list of needed rows, not the canvas.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warp-
 // uniform code, one elected lane issues), warps 2..5 / 6..9 = epilogue group of stream 0 / 1
-// (TMEM -> registers -> zero the slot -> bias/PReLU -> fp16 -> swizzled smem -> TMA store, or for
-// the tail: bias -> PixelShuffle + residual -> u8 -> global).
+// (TMEM -> registers -> zero the slot -> bias/PReLU -> fp16 -> swizzled smem -> one TMA store per warp: every warp
+// ships the quarter of the row it wrote and waits only for its own previous read-out; or for the tail: bias ->
+// PixelShuffle + residual -> u8 -> global).
 #include "kernels.h"
 
 #include <algorithm>
