@@ -385,6 +385,18 @@ int run_segments(const Options& o, const reve_model* model) {
         remove_dir(temp + "/out_frames/" + std::to_string(sg.index));
     }
 
+    // A last segment of ZERO frames exists whenever frame_count % segment_size == 1 (reference lib.rs:282-289 subtracts
+    // one from the remainder): nothing to export, upscale or encode, and no part file to wait for.
+    for (size_t i = 0; i < video.segments.size();) {
+        if (video.segments[i].size <= 0) {
+            std::fprintf(stderr, "segment %ld holds no frames (frame_count %% segment_size == 1): nothing to do\n", video.segments[i].index);
+            video.segments.erase(video.segments.begin() + static_cast<long>(i));
+        } else ++i;
+    }
+    {
+        std::string e;
+        if (!video.save(state_file, e)) { std::fprintf(stderr, "error: %s\n", e.c_str()); return 1; }
+    }
     std::mutex qm;                                   // guards the queue, the state and its file
     std::deque<reve_host::Segment> queue(video.segments.begin(), video.segments.end());
     std::atomic<bool> failed{false};

@@ -240,3 +240,18 @@ def test_segment_scheduler_on_the_gpu_two_lanes(exe, tmp_path):
         got = cv2.imread(str(keep / str(i) / f"frame{k + 1:08d}.png"), cv2.IMREAD_COLOR)[:, :, ::-1]
         par = srvgg.parity(got, srvgg.upscale(f, wts, tile=200, prepad=10))
         assert par["within1"] >= 0.999 and par["psnr"] >= 50, (i, k, par)
+
+
+def test_segment_scheduler_skips_the_empty_last_segment(exe, tmp_path):
+    """frame_count % segment_size == 1 makes the reference's last segment ZERO frames long (lib.rs:282-289: remainder - 1;
+    `reve_b200.last_segment_size(1001, 1000) == 0`).  There is nothing to export, upscale or encode for it: the
+    scheduler drops it instead of running ffmpeg with `-vframes 0` and waiting for a part file that cannot exist."""
+    st = _video_temp(tmp_path, frame_count=2001, segment_size=1000)
+    assert [n for _, n in st.segments] == [1000, 1000, 0]
+    r = subprocess.run([exe, "--segments", str(tmp_path), "--schedule-only", "-g", "0,1",
+                        "--export-cmd", "test {size} -gt 0", "--encode-cmd", "test {size} -gt 0 && echo ok > {part}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "segment 2 holds no frames" in r.stderr
+    assert sorted(p.name for p in (tmp_path / "video_parts").iterdir()) == ["0.mp4", "1.mp4"]
+    assert reve_b200.VideoState.from_json((tmp_path / "video.temp").read_text()).segments == []
