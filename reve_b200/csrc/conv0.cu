@@ -69,9 +69,6 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t addr, uint32_t lbo, 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __global__ void __launch_bounds__(kThreads, 1)
 conv0_umma_kernel(const __grid_constant__ CUtensorMap out_map, const __grid_constant__ Conv0Params p) {
     // out_map: the output canvas as a flat [pixels][64 ch] tensor with a 32-pixel box: every epilogue warp stores the

@@ -209,15 +209,15 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t lo) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+[[maybe_unused]] __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void st_shared_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory"); }
-__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+[[maybe_unused]] __device__ __forceinline__ void st_shared_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+[[maybe_unused]] __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory"); }
+[[maybe_unused]] __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -1228,7 +1228,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         ChainCursor cur(rspace, lo[grp], hi[grp], ext);
         const int n_events = U[grp];
         const int mlo = 1 + j, mhi = kBoxPx - 2 - j;     // valid output pixels of this layer
-        const bool gleader = (q == 0 && lane == 0);
+        [[maybe_unused]] const bool gleader = (q == 0 && lane == 0);   // (REVE_LAST_QUARTERS = 0 path)
         const float* const bias = p.bias[j];
         const __half2* const slope2 = p.slope2[j];
         int sent = 0;
