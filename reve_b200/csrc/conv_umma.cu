@@ -1159,7 +1159,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             uint32_t w_row = w_lo + (2 - (k + 1) % 3) * kRot;
             asm volatile("" : "+r"(w_row));
             const uint32_t d = tmem_base + s * kBank;
-            if (p.trace && chain == static_cast<unsigned>(p.trace_chain) && i >= 200 && i < 692 && lane == 0) p.trace[j * 512 + i - 200] = clock64();
+            if (p.trace && chain == static_cast<unsigned>(p.trace_chain) && i >= 200 && i < 684 && lane == 0) p.trace[j * 512 + i - 200] = clock64();
             if (elected) {
 #pragma unroll
                 for (int dxk = 0; dxk < 4; ++dxk)
@@ -1234,6 +1234,7 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         int sent = 0;
         int seg_xb = 0;
         bool seg_colok = false;
+        long long ta_acc = 0, ta_drain = 0, ta_wait = 0, ta_out = 0, ta_n = 0;   // trace accumulators (registers)
         for (int e = 0; e < n_events; ++e) {
             bool valid = false, keep = false;
             int pr = 0;
@@ -1251,7 +1252,12 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                 if (valid) keep = seg_colok && (pr >= 0) && (pr < CH) && (p.rowflag[pr] != 0);
             }
             const int slot = e % 3;
+            // (trace: where warp 0 of group 0 of the traced chain spends an event)
+            long long* const etr = (p.trace && chain == static_cast<unsigned>(p.trace_chain) && grp == 0 && q == 0 && lane == 0)
+                                       ? p.trace + j * 512 + 484 : nullptr;
+            const long long e0 = etr ? clock64() : 0;
             mbar_wait(base + kBarAccFull + 8 * (grp * 3 + slot), (e / 3) & 1, dbg, TAG_ACC_FULL, e);
+            const long long e1 = etr ? clock64() : 0;
             tc_fence_after();
             uint32_t acc[NG];
             if (valid) {
@@ -1268,6 +1274,8 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(base + kBarAccEmpty + 8 * (grp * 3 + slot));
+            const long long e2 = etr ? clock64() : 0;
+            if (etr) { ta_acc += e1 - e0; ta_drain += e2 - e1; ta_n += 1; }
             if (!valid) continue;
 
             const uint32_t stg = base + kOffStage + grp * kRowBytes;
@@ -1288,6 +1296,8 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
             }
             // last layer: box rows mlo..mhi become staging rows 0..P-1 (the stored box); other layers hand on the
             // whole 128-row tile in place (rows outside the valid range as zeros)
+            const long long e3 = etr ? clock64() : 0;
+            if (etr) ta_wait += e3 - e2;                       // waiting for the staging quarter's read-out
             const bool writes = last ? (m >= mlo && m <= mhi) : true;
             if (writes) {
 #if REVE_LAST_QUARTERS
@@ -1343,7 +1353,12 @@ conv3x3_chain_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
                 if (lane == 0) mbar_arrive(base + kBarStgFull + 8 * grp);
 #endif
             }
+            if (etr) ta_out += clock64() - e3;                 // bias / PReLU / pack / staging writes / fence / hand-off
             ++sent;
+        }
+        if (p.trace && chain == static_cast<unsigned>(p.trace_chain) && grp == 0 && q == 0 && lane == 0) {
+            long long* const t = p.trace + j * 512 + 484;
+            t[0] = ta_acc; t[1] = ta_drain; t[2] = ta_wait; t[3] = ta_out; t[4] = ta_n;
         }
     }
 

@@ -22,7 +22,7 @@ for _ in range(3):
 tr = np.zeros(4096, np.int64)
 assert _lib.load().reve_debug_trace(up._h, tr.ctypes.data, 4096) == 0
 for j in range(L):
-    t = tr[512 * j:512 * j + 492]
+    t = tr[512 * j:512 * j + 484]
     t = t[t > 0]
     d = np.diff(t)
     d = d[(d > 0) & (d < 100000)]     # (entries of an earlier launch with more steps may linger at the end)
@@ -34,6 +34,11 @@ for j in range(L):
         line += f" | courier/row: wait_full {c[0] / c[3]:.0f} store {c[1] / c[3]:.0f} publish {c[2] / c[3]:.0f}"
     if c[7]:
         line += f" | loader/step: retire {c[4] / c[7]:.0f} poll {c[5] / c[7]:.0f} a_empty {c[6] / c[7]:.0f}"
+    ep = tr[512 * j + 484:512 * j + 489]
+    if ep[4]:
+        n = ep[4]
+        line += (f" | epilogue warp 0/event: wait acc {ep[0] / n:.0f} drain {ep[1] / n:.0f} wait quarter {ep[2] / n:.0f} "
+                 f"output {ep[3] / n:.0f}")
     m = tr[512 * j + 492:512 * j + 496]
     if c[7]:
         runs = 3     # the counters accumulate over the three traced launches above
