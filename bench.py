@@ -491,9 +491,11 @@ def run_ours(args):
                          "frames_per_launch": frames_per_launch, "layers_per_launch": layers_per_launch,
                          "ms_per_frame": {"conv0": conv0_ms, "body_x16": pr["ms_body"] / frames_timed, "tail": tail_ms}},
             "roofline_others": {
-                "conv0_umma_kernel": {"bound": "hbm", "achieved": conv0_bytes / (conv0_ms * 1e-3) / 1e9 if conv0_ms else None,
+                "conv0_rows_kernel": {"bound": "hbm", "achieved": conv0_bytes / (conv0_ms * 1e-3) / 1e9 if conv0_ms else None,
                                       "peak": hbm, "unit": "GB/s", "frac": conv0_bytes / (conv0_ms * 1e-3) / 1e9 / hbm if conv0_ms else None,
-                                      "algorithmic_bytes_per_frame": conv0_bytes},
+                                      "algorithmic_bytes_per_frame": conv0_bytes,
+                                      "note": "a write stream (128 B written, 3 B read per canvas pixel); the write-only ceiling with this access "
+                                              "pattern is 6.06 TB/s (profiles/r02_store_paths.txt)"},
                 "conv3x3_umma_kernel<tail>": {"bound": "hbm", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9 if tail_ms else None,
                                               "peak": hbm, "unit": "GB/s", "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / hbm if tail_ms else None,
                                               "algorithmic_bytes_per_frame": tail_bytes},

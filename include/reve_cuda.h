@@ -109,6 +109,7 @@ int reve_ctx_create(int device, const reve_model* m, int in_w, int in_h, int til
 #define REVE_DBG_ALIAS_ROWS 16u     /* canvas rows alias each other in L2: timing experiment, results are WRONG */
 #define REVE_DBG_FAULT 32u          /* chained kernel waits for a row that never comes: exercises the watchdog path */
 #define REVE_DBG_EQUAL_SPLIT 64u    /* chained kernel: equal blocks per chain instead of the self-balancing split */
+#define REVE_DBG_CONV0_IM2COL 128u  /* first conv: the K = 27 im2col kernel (conv0.cu) instead of the row-streaming one (conv0_rows.cu) */
 typedef struct reve_ctx_options {
     uint32_t struct_size;      /* sizeof(reve_ctx_options) */
     uint32_t flags;            /* REVE_CTX_* */

@@ -74,6 +74,7 @@ struct reve_ctx {
     CUtensorMap map_in[2], map_out[2], map_out_q[2];   // input boxes of 128 px; output boxes of 31 px (map_out) and 32 px (map_out_q)
     CUtensorMap map_flat0;   // act[0] as a flat [pixels][64] tensor (conv0 output tiles of 128 pixels)
     void* d_w0 = nullptr;    // conv0 B operand
+    void* d_w0_rows = nullptr;   // conv0, row-streaming kernel: three per-tap B operands
     Conv0Params c0;
     ConvParams body[kNumBody];
     ConvParams tail;
@@ -236,8 +237,13 @@ int enqueue_batch(reve_ctx* ctx, int n, const uint8_t* const* d_in, long long in
     for (int f = 0; f < n; ++f) c0.src[f] = d_in[f];
     c0.src_stride = in_stride;
     {
-        const long long tiles0 = (static_cast<long long>(c0.canvas_w) * ch + 127) / 128;
-        CK(ctx, launch_conv0(ctx->s_comp, static_cast<int>(tiles0 < ctx->sm_count ? tiles0 : ctx->sm_count), ctx->map_flat0, c0));
+        if (!(ctx->opt.debug_flags & REVE_DBG_CONV0_IM2COL)) {
+            const long long rows0 = static_cast<long long>((c0.canvas_w + 127) / 128) * ch;
+            CK(ctx, launch_conv0_rows(ctx->s_comp, static_cast<int>(rows0 < ctx->sm_count ? rows0 : ctx->sm_count), ctx->map_out_q[0], c0));
+        } else {
+            const long long tiles0 = (static_cast<long long>(c0.canvas_w) * ch + 127) / 128;
+            CK(ctx, launch_conv0(ctx->s_comp, static_cast<int>(tiles0 < ctx->sm_count ? tiles0 : ctx->sm_count), ctx->map_flat0, c0));
+        }
     }
     ctx->prof.launches_conv0++;
     prof_mark(ctx, 0);
@@ -416,6 +422,7 @@ void destroy_ctx(reve_ctx* ctx) {
     for (auto& rm : ctx->rowmaps) cudaFree(rm.d);
     for (void* p : ctx->d_wblob) cudaFree(p);
     cudaFree(ctx->d_w0);
+    cudaFree(ctx->d_w0_rows);
     cudaFree(ctx->d_trace);
     cudaFree(ctx->d_chain_scratch);
     cudaFree(ctx->d_chain_flags);
@@ -455,6 +462,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
 
     CK(ctx, conv_kernels_init());
     CK(ctx, conv0_kernel_init());
+    CK(ctx, conv0_rows_kernel_init());
     CK(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -571,6 +579,9 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
         std::vector<uint16_t> blob(conv0_weight_blob_bytes() / 2);
         pack_conv0_weights(m.conv[0].w.data(), blob.data());
         if ((rc = upload(ctx, &ctx->d_w0, blob.data(), blob.size() * 2))) return rc;
+        std::vector<uint16_t> rows(conv0_rows_weight_blob_bytes() / 2);
+        pack_conv0_rows_weights(m.conv[0].w.data(), rows.data());
+        if ((rc = upload(ctx, &ctx->d_w0_rows, rows.data(), rows.size() * 2))) return rc;
     }
     const int tail_ng = m.scale == 2 ? 16 : (m.scale == 3 ? 32 : 48);
     for (int k = 1; k < kNumConv; ++k) {
@@ -592,6 +603,7 @@ int create_ctx(reve_ctx* ctx, int device, const Model& m, int in_w, int in_h, in
     c0.src_y = ctx->d_srcy;
     c0.row_frame = ctx->d_rowframe;
     c0.weights = ctx->d_w0;
+    c0.weights_rows = ctx->d_w0_rows;
     c0.dbg = ctx->dbg_dev;
     for (int co = 0; co < 64; ++co) {
         c0.bias[co] = m.conv[0].b[co];

@@ -106,6 +106,7 @@ struct Conv0Params {
     const int* src_y;
     const int* row_frame;      // [canvas_h] frame of the batch (-1 = gap row)
     const void* weights;       // B operand blob (pack_conv0_weights)
+    const void* weights_rows;  // the three per-tap B operands of the row-streaming kernel (pack_conv0_rows_weights)
     DebugBlock* dbg;
     float bias[64];
     float slope[64];
@@ -144,5 +145,11 @@ size_t conv0_weight_blob_bytes();
 void pack_conv0_weights(const float* w_oihw, uint16_t* blob);
 cudaError_t conv0_kernel_init();
 cudaError_t launch_conv0(cudaStream_t st, int grid, const CUtensorMap& out_map, const Conv0Params& p);
+// Row-streaming variant (conv0_rows.cu): every input row gathered once, three per-tap MMAs; out_map_q = the output canvas
+// with 32-pixel boxes.  grid <= strips * rows.
+size_t conv0_rows_weight_blob_bytes();
+void pack_conv0_rows_weights(const float* w_oihw, uint16_t* blob);
+cudaError_t conv0_rows_kernel_init();
+cudaError_t launch_conv0_rows(cudaStream_t st, int grid, const CUtensorMap& out_map_q, const Conv0Params& p);
 
 }  // namespace reve

@@ -21,6 +21,7 @@ FMT_RGB24, FMT_YUV420P10LE_BT601, FMT_YUV420P10LE_BT709 = 0, 1, 2
 CTX_SHARED_DEVICE = 1
 # test hooks (reve_ctx_options.debug_flags, include/reve_cuda.h)
 DBG_NO_REVERSE, DBG_CTA_PAIRS, DBG_SWAP_PAIR_B, DBG_ALL_ROWS, DBG_ALIAS_ROWS, DBG_FAULT, DBG_EQUAL_SPLIT = 1, 2, 4, 8, 16, 32, 64
+DBG_CONV0_IM2COL = 128
 
 
 class ReveError(RuntimeError):

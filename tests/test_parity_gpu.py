@@ -742,3 +742,57 @@ def test_standalone_unpack_and_pack_kernels_are_bit_exact(w, h, scale, tile):
         want = srvgg.quantise(y.astype(np.float16).astype(np.float32)[np.ix_(rows, cols)])
         assert got.shape == want.shape == (h * scale, w * scale, 3)
         assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The two first-conv kernels: the row-streaming one (conv0_rows.cu, default) and the K = 27 im2col one (conv0.cu,
+# DBG_CONV0_IM2COL).  Same function, different accumulation order: features agree to an fp16 ulp, frames to 1 LSB, both
+# meet the oracle.  Cases: one CTA (every ring lap), ragged widths, tiles (gap rows / columns), frames stacked four to a
+# canvas (gap rows between frames), and a canvas whose geometry tables do not fit shared memory (global-table path).
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,scale,tile,grid", [
+    (100, 30, 2, 0, 1), (129, 17, 2, 0, 0), (300, 200, 2, 64, 0), (137, 91, 3, 50, 0), (150, 90, 4, 0, 3), (11, 11, 4, 0, 0),
+    (640, 480, 2, 200, 0),
+])
+def test_first_conv_kernels_agree_and_meet_the_oracle(w, h, scale, tile, grid):
+    wts = srvgg.make_weights(scale, 77)
+    model = reve_b200.Model.random(scale, 77)
+    frame = srvgg.synthetic_frame(w, h, 12, "random")
+    ref = oracle_canvas(frame, wts, tile, 10, 1)
+    got = {}
+    for name, flags in (("rows", 0), ("im2col", reve_b200.DBG_CONV0_IM2COL)):
+        with reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=2, debug_flags=flags, debug_grid=grid) as up:
+            feat = up.debug_features(frame, 1)
+            assert feat.shape == ref.shape
+            assert feature_report(feat, ref, np.ones(ref.shape[0], bool))["bad_frac"] == 0.0, name
+            got[name] = (feat, up.upscale(frame))
+    d = np.abs(got["rows"][0] - got["im2col"][0])
+    assert d.max() <= 2e-3 and (d == 0).mean() > 0.999, (float(d.max()), float((d == 0).mean()))
+    assert np.abs(got["rows"][1].astype(int) - got["im2col"][1].astype(int)).max() <= 1
+    check(got["rows"][1], srvgg.upscale(frame, wts, tile=tile, prepad=10))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,tile", [(300, 200, 64), (48, 3000, 0)])
+def test_first_conv_on_stacked_frames_and_global_tables(w, h, tile):
+    """Four different frames per launch set (one canvas, gap rows between the frames).  48 x 3000 makes the stacked
+    canvas 12 083 rows tall: its row tables (2 ints per row) exceed the 48 KB the kernels cache in shared memory, so the
+    global-memory table path runs."""
+    import torch
+    scale, n = 2, 4
+    wts = srvgg.make_weights(scale, 5)
+    model = reve_b200.Model.random(scale, 5)
+    frames = np.stack([srvgg.synthetic_frame(w, h, 30 + i, "random" if i % 2 else "edges") for i in range(n)])
+    outs = {}
+    for name, flags in (("rows", 0), ("im2col", reve_b200.DBG_CONV0_IM2COL)):
+        with reve_b200.Upscaler(model, w, h, tile=tile, prepad=10, ring_depth=4, debug_flags=flags) as up:
+            assert up.launch_info()["batch"] == n
+            d_in = torch.from_numpy(frames).cuda()
+            d_out = torch.zeros((n, h * scale, w * scale, 3), dtype=torch.uint8, device="cuda")
+            up.upscale_device(d_in.data_ptr(), d_out.data_ptr(), n)
+            up.sync()
+            outs[name] = d_out.cpu().numpy()
+    assert np.abs(outs["rows"].astype(int) - outs["im2col"].astype(int)).max() <= 1
+    for i in (0, n - 1):
+        check(outs["rows"][i], srvgg.upscale(frames[i], wts, tile=tile, prepad=10))
