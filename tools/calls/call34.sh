@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU call 34 of round 2: HEAD with the row-streaming first conv: whole suite, sanitizers, smoke, bench at every workload, launch list.
+# GPU call 34 of round 2 (run again as call 37 after the two-rows-per-step change): HEAD with the row-streaming first conv: whole suite, sanitizers, smoke, bench at every workload, launch list.
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
