@@ -51,11 +51,39 @@ def metric_name(workload: str) -> str:
     return "frames/s animevideov3 x2 1080p->4K" if workload == "1080p_x2" else f"frames/s animevideov3 x{s} {h}p->{h * s}p"
 
 
+def make_frame(kind: str, w: int, h: int, seed: int) -> np.ndarray:
+    """Synthetic input frames.  'noise' (default, and what every committed number uses unless it says otherwise): uniform u8
+    noise -- the worst case for an energy-bound kernel, every operand bit toggles.  'edges': anime-like frames
+    (a gradient, flat regions with hard edges, line art).  'real': the decoded frame of the reference's demo clip held by
+    tests/golden (640x480), tiled and shifted to the workload's size.  The arithmetic is identical; what changes is the
+    switching activity, hence the power, hence the clock the 1000 W cap allows (profiles/r02_notes.md section 17)."""
+    if kind == "noise":
+        return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if kind == "edges":
+        rng = np.random.default_rng(seed)
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.empty((h, w, 3), np.uint8)
+        img[..., 0] = xx * 255 // max(1, w - 1)                      # a gradient background
+        img[..., 1] = yy * 255 // max(1, h - 1)
+        img[..., 2] = 128
+        for _ in range(40):                                          # flat regions with hard edges
+            x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
+            img[y0:y0 + int(rng.integers(h // 20, h // 3)), x0:x0 + int(rng.integers(w // 20, w // 3))] = rng.integers(0, 256, 3)
+        img[(xx // 7 + yy // 5) % 11 == 0] = 0                       # line art
+        return img
+    g = np.load(os.path.join(ROOT, "tests", "golden", "x2_tile200_real_onepiece_480p.npz"))
+    src = g["frame"]
+    reps = (-(-h // src.shape[0]) + 1, -(-w // src.shape[1]) + 1, 1)
+    big = np.tile(src, reps)
+    dy, dx = (seed * 37) % src.shape[0], (seed * 101) % src.shape[1]
+    return np.ascontiguousarray(big[dy:dy + h, dx:dx + w])
+
+
 def config_block(args, world: int, parallelism: str) -> dict:
     """The same keys on both arms (ours / reference), so that the driver's same-config check compares like with like."""
     w, h, s, cfg = WORKLOADS[args.workload]
     return {"workload": f"{args.workload}: {cfg}", "frame": [w, h], "scale": s, "tile": args.tile, "prepad": args.prepad,
-            "frames_per_step": args.batch, "ring_depth": 8, "weights": WEIGHTS_NOTE,
+            "frames_per_step": args.batch, "ring_depth": 8, "weights": WEIGHTS_NOTE, "frames": args.frames,
             "l2": f"working set per launch set (2 fp16 activation canvases of 4 stacked frames) exceeds the 126 MB L2; "
                   f"{args.batch} distinct frames cycled",
             "parallelism": parallelism}
@@ -230,8 +258,7 @@ class Lane:
         self.up = reve_b200.Upscaler(self.model, self.w, self.h, tile=args.tile, prepad=args.prepad, device=dev, ring_depth=8,
                                      shared_device=args.shared_device)
         B = args.batch
-        self.frames = np.stack([np.random.default_rng(seed_base + i).integers(0, 256, (self.h, self.w, 3), dtype=np.uint8)
-                                for i in range(min(B, 8))])
+        self.frames = np.stack([make_frame(args.frames, self.w, self.h, seed_base + i) for i in range(min(B, 8))])
         self.nres = len(self.frames)
         self.d_in = torch.from_numpy(self.frames).to(f"cuda:{dev}")
         self.d_out = torch.empty((self.nres, self.h * self.scale, self.w * self.scale, 3), dtype=torch.uint8, device=f"cuda:{dev}")
@@ -547,6 +574,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p_x2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=12, help="frames per step (20 steps x 12 = 240 frames per timed region)")
+    ap.add_argument("--frames", default="noise", choices=["noise", "edges", "real"],
+                    help="synthetic input: uniform noise (default, worst case for power), anime-like flat regions + line art, or the reference's demo frame tiled")
     ap.add_argument("--tile", type=int, default=200, help="upstream tile size (0 = whole frame)")
     ap.add_argument("--prepad", type=int, default=10)
     ap.add_argument("--model-dir", default="models")
