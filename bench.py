@@ -83,7 +83,7 @@ def config_block(args, world: int, parallelism: str) -> dict:
     """The same keys on both arms (ours / reference), so that the driver's same-config check compares like with like."""
     w, h, s, cfg = WORKLOADS[args.workload]
     return {"workload": f"{args.workload}: {cfg}", "frame": [w, h], "scale": s, "tile": args.tile, "prepad": args.prepad,
-            "frames_per_step": args.batch, "ring_depth": 8, "weights": WEIGHTS_NOTE, "frames": args.frames,
+            "frames_per_step": args.batch, "ring_depth": 8, "weights": WEIGHTS_NOTE, "frames": getattr(args, "frames", "noise"),
             "l2": f"working set per launch set (2 fp16 activation canvases of 4 stacked frames) exceeds the 126 MB L2; "
                   f"{args.batch} distinct frames cycled",
             "parallelism": parallelism}
