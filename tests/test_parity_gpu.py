@@ -796,3 +796,29 @@ def test_first_conv_on_stacked_frames_and_global_tables(w, h, tile):
     assert np.abs(outs["rows"].astype(int) - outs["im2col"].astype(int)).max() <= 1
     for i in (0, n - 1):
         check(outs["rows"][i], srvgg.upscale(frames[i], wts, tile=tile, prepad=10))
+
+
+@pytest.mark.gpu
+def test_4k_input_tile_locality_and_window_oracle():
+    """The largest realistic input (3840x2160 -> 7680x4320; the canvas is 4 x a 1080p one, 209 tiles): no oracle run of
+    the whole frame (a minute of CPU), but properties that do not depend on the size.  Deterministic; a tile's output
+    depends only on the tile and its 10 px of real neighbours, so (a) the first 6 x 10 tiles are bit-identical to the
+    same tiles of a 2010 x 1210 crop -- a different canvas, different strips, different CTA ranges -- and (b) an interior
+    tile far from the origin meets the oracle run on its 220 x 220 window."""
+    w, h, scale = 3840, 2160, 2
+    wts = srvgg.make_weights(scale, 1234)
+    model = reve_b200.Model.random(scale, 1234)
+    frame = srvgg.synthetic_frame(w, h, 91, "edges")
+    frame[::2, ::3] = srvgg.synthetic_frame(w, h, 92, "random")[::2, ::3]
+    with reve_b200.Upscaler(model, w, h, tile=200, prepad=10, ring_depth=2) as up:
+        out = up.upscale(frame)
+        assert np.array_equal(out, up.upscale(frame))
+    assert out.shape == (h * scale, w * scale, 3)
+    crop = np.ascontiguousarray(frame[:1210, :2010])
+    with reve_b200.Upscaler(model, 2010, 1210, tile=200, prepad=10, ring_depth=2) as up:
+        small = up.upscale(crop)
+    assert np.array_equal(out[:2400, :4000], small[:2400, :4000])
+    win = np.ascontiguousarray(frame[1390:1610, 2990:3210])                    # tile (7, 15) + 10 px of real neighbours
+    x = (win.astype(np.float32) * np.float32(1 / 255.0)).transpose(2, 0, 1)
+    ref_win = srvgg.quantise(srvgg.forward(x, wts)[:, 20:-20, 20:-20].transpose(1, 2, 0))
+    check(out[2800:3200, 6000:6400], ref_win)
