@@ -154,7 +154,7 @@ conv0_rows_kernel(const __grid_constant__ CUtensorMap out_map_q, const __grid_co
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kTmemPtr);
 
     const int n_strips = (CW + 127) / 128;
-    const long long total = static_cast<long long>(n_strips) * CHh;   // launch_conv0_rows checks that it fits an int
+    const long long total = static_cast<long long>(n_strips) * CHh;   // fits an int: activation canvases are capped at 6 GB (api.cu), i.e. 47 M pixels
     Walk walk{static_cast<int>(total * blockIdx.x / gridDim.x), static_cast<int>(total * (blockIdx.x + 1) / gridDim.x), CHh};
     int strip, ya, n;
     // A segment of n output rows is ceil(n/2) PAIRS of rows; step s (0 .. pairs) takes input rows ya+2s-1 and ya+2s,
